@@ -1,0 +1,94 @@
+"""ctypes loader for libtezgpu.so.  Fails loudly: there is no Python/CPU fallback for the hot path."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtezgpu.so")
+
+
+class Conf(C.Structure):
+    """tezgpu_conf (include/tezgpu.h)"""
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("num_partitions", C.c_int32),
+                ("comparator", C.c_int32), ("partitioner", C.c_int32), ("rle_policy", C.c_int32),
+                ("send_empty_partition_details", C.c_int32), ("sorter_impl", C.c_int32),
+                ("fixed_key_len", C.c_uint32), ("fixed_val_len", C.c_uint32), ("mem_budget_bytes", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    """tezgpu_stats (include/tezgpu.h)"""
+    _fields_ = [("output_records", C.c_int64), ("output_bytes", C.c_int64), ("output_bytes_with_overhead", C.c_int64),
+                ("output_bytes_physical", C.c_int64), ("spilled_records", C.c_int64), ("file_out_bytes", C.c_int64),
+                ("num_spills", C.c_int32), ("rle_used", C.c_int32), ("adjacent_equal_keys", C.c_int64),
+                ("tie_records", C.c_int64), ("ms_stage", C.c_float), ("ms_sort", C.c_float), ("ms_ties", C.c_float),
+                ("ms_emit", C.c_float), ("ms_total", C.c_float), ("kernel_launches", C.c_int32), ("reserved1", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
+
+
+class Segment(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("len", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class KvIndex(C.Structure):
+    _fields_ = [("key_off", C.c_uint32), ("key_len", C.c_uint32), ("val_off", C.c_uint32), ("val_len", C.c_uint32),
+                ("same_key", C.c_uint32)]
+
+
+# every symbol include/tezgpu.h declares: (name, restype, argtypes)
+_V, _P = C.c_void_p, C.POINTER
+SYMBOLS = [
+    ("tezgpu_last_error", C.c_char_p, []),
+    ("tezgpu_abi_version", C.c_int32, []),
+    ("tezgpu_device_count", C.c_int32, []),
+    ("tezgpu_sorter_create", C.c_int32, [_P(Conf), _P(_V)]),
+    ("tezgpu_sorter_collect_batch", C.c_int32, [_V, _V, C.c_uint64, _V, _V, _V, _V, C.c_uint32]),
+    ("tezgpu_sorter_collect_fixed", C.c_int32, [_V, _V, _V, C.c_uint64]),
+    ("tezgpu_sorter_flush", C.c_int32, [_V, C.c_char_p, C.c_char_p, _V, _P(Stats)]),
+    ("tezgpu_sorter_flush_to_memory", C.c_int32, [_V, _V, C.c_uint64, _P(C.c_uint64), _V, _V, _P(Stats)]),
+    ("tezgpu_sorter_output_bound", C.c_uint64, [_V]),
+    ("tezgpu_sorter_destroy", C.c_int32, [_V]),
+    ("tezgpu_sorter_sort_device_fixed", C.c_int32, [_V, _V, _V, C.c_uint64, _V, C.c_uint64, _P(C.c_uint64), _V, _P(Stats)]),
+    ("tezgpu_sorter_stream", _V, [_V]),
+    ("tezgpu_debug_crc_emulate", C.c_uint32, [_V, C.c_uint64, C.c_uint32, C.c_uint32]),
+    ("tezgpu_merge_open", C.c_int32, [_P(Conf), _P(Segment), C.c_uint32, _P(_V)]),
+    ("tezgpu_merge_counts", C.c_int32, [_V, _P(C.c_uint64), _P(C.c_uint64)]),
+    ("tezgpu_merge_next_batch", C.c_int32, [_V, _V, C.c_uint64, _P(KvIndex), C.c_uint32, _P(C.c_uint32)]),
+    ("tezgpu_merge_write_ifile", C.c_int32, [_V, C.c_char_p, _V, C.c_uint64, C.c_int32, _P(C.c_int64), _P(C.c_int64), _P(Stats)]),
+    ("tezgpu_merge_output_bound", C.c_uint64, [_V]),
+    ("tezgpu_merge_write_ifile_device", C.c_int32, [_V, _V, C.c_uint64, C.c_int32, _P(C.c_int64), _P(C.c_int64), _P(Stats)]),
+    ("tezgpu_merge_stream", _V, [_V]),
+    ("tezgpu_merge_close", C.c_int32, [_V]),
+]
+
+_lib = None
+
+
+def load():
+    """Returns the loaded library; raises if the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "tez_b200: %s is missing -- build it with `python -m tez_b200.build` "
+                "(the hot path has no Python or CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)  # AttributeError if the ABI and the header drift apart
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class TezGpuError(IOError):
+    """Every failure of the path surfaces as an IOException in the reference; same here."""
+
+    def __init__(self, code, msg):
+        super().__init__("tezgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+def check(rc):
+    if rc != 0:
+        raise TezGpuError(rc, load().tezgpu_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,79 @@
+// crc32.cuh -- CRC-32 (poly 0xEDB88320, the IFileOutputStream / PureJavaCrc32 checksum,
+// SORT/IFileOutputStream.java:53-90, SORT/TezSpillRecord.java:111-146) for parallel use on the device.
+//
+// The per-segment checksum of an IFile body is sequential by definition; on the device every emit tile computes the
+// standard CRC of its own bytes and folds it into the segment checksum with
+//     crc(A || B) = crc(A) * x^(8*len(B))  xor  crc(B)          (GF(2)[x] / P, reflected bit order)
+// so tiles combine with one atomicXor each.  Powers of x come from three 4096-entry tables (x^(8*a0),
+// x^(8*4096*a1), x^(8*2^24*a2)) computed once on the host.
+#pragma once
+#include "common.cuh"
+
+namespace tezgpu {
+
+constexpr uint32_t CRC_POLY = 0xEDB88320u;
+
+// a(x) * b(x) mod P, reflected representation (bit 31 = x^0)
+__host__ __device__ __forceinline__ uint32_t crc_multmodp(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+#pragma unroll 4
+  for (int i = 0; i < 32; i++) {
+    p ^= b & (0u - ((a >> (31 - i)) & 1u));
+    b = (b >> 1) ^ (CRC_POLY & (0u - (b & 1u)));
+  }
+  return p;
+}
+
+struct CrcTables {
+  uint32_t slice[4][256];   // slice-by-4 byte tables: slice[k][b] = (b * x^(8*(k+1))) mod P, k = 0 is the classic table
+  uint32_t adv[4][256];     // multiply-by-x^(32*EMIT_CRC_STRIDE_WORDS) byte tables (interleaved per-thread streams)
+  uint32_t pow_word[512];   // x^(32*j), j < 512
+  uint32_t pow0[4096];      // x^(8*a)
+  uint32_t pow1[4096];      // x^(8*4096*a)
+  uint32_t pow2[4096];      // x^(8*2^24*a)
+};
+
+static inline uint32_t crc_host_xpow8(uint64_t nbytes) {
+  // x^(8*nbytes) mod P by square-and-multiply
+  uint32_t result = 0x80000000u;  // x^0
+  uint32_t base = 0x00800000u;    // x^8
+  while (nbytes) {
+    if (nbytes & 1) result = crc_multmodp(result, base);
+    base = crc_multmodp(base, base);
+    nbytes >>= 1;
+  }
+  return result;
+}
+
+static inline void crc_build_tables(CrcTables &t, int stride_words) {
+  for (uint32_t i = 0; i < 256; i++) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; k++) c = (c & 1) ? CRC_POLY ^ (c >> 1) : (c >> 1);
+    t.slice[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; i++)
+    for (int k = 1; k < 4; k++) t.slice[k][i] = (t.slice[k - 1][i] >> 8) ^ t.slice[0][t.slice[k - 1][i] & 0xFF];
+  // adv[k][b] = (b << 8k) * x^(32*stride_words): a register value v with byte b at bits [8k,8k+8)
+  uint32_t xs = crc_host_xpow8((uint64_t)4 * (uint64_t)stride_words);
+  for (int k = 0; k < 4; k++)
+    for (uint32_t b = 0; b < 256; b++) t.adv[k][b] = crc_multmodp(b << (8 * k), xs);
+  for (int j = 0; j < 512; j++) t.pow_word[j] = crc_host_xpow8((uint64_t)4 * (uint64_t)j);
+  uint32_t s0 = crc_host_xpow8(1), s1 = crc_host_xpow8(4096), s2 = crc_host_xpow8(1ull << 24);
+  t.pow0[0] = t.pow1[0] = t.pow2[0] = 0x80000000u;
+  for (int a = 1; a < 4096; a++) {
+    t.pow0[a] = crc_multmodp(t.pow0[a - 1], s0);
+    t.pow1[a] = crc_multmodp(t.pow1[a - 1], s1);
+    t.pow2[a] = crc_multmodp(t.pow2[a - 1], s2);
+  }
+}
+
+// crc * x^(8*nbytes) for nbytes < 2^36
+__device__ __forceinline__ uint32_t crc_shift_bytes(const CrcTables *__restrict__ t, uint32_t crc, uint64_t nbytes) {
+  uint32_t a0 = (uint32_t)(nbytes & 4095), a1 = (uint32_t)((nbytes >> 12) & 4095), a2 = (uint32_t)((nbytes >> 24) & 4095);
+  if (a0) crc = crc_multmodp(crc, t->pow0[a0]);
+  if (a1) crc = crc_multmodp(crc, t->pow1[a1]);
+  if (a2) crc = crc_multmodp(crc, t->pow2[a2]);
+  return crc;
+}
+
+}  // namespace tezgpu

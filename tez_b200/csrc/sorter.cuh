@@ -1,0 +1,314 @@
+// sorter.cuh -- host orchestration of the device sort pipeline (one "spill" covering everything collected:
+// HBM is the sort buffer, so this is always the numSpills==1 branch of PipelinedSorter.flush, :730-756).
+#pragma once
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/tezgpu.h"
+#include "device_util.h"
+#include "sorter_kernels.cuh"
+
+namespace tezgpu {
+
+static inline int partition_bits(int P) {
+  int b = 0;
+  while ((1ll << b) < (long long)P) b++;
+  return b;
+}
+
+// per-device constant tables (CRC), created once
+struct DeviceConstants {
+  CrcTables *d_crc = nullptr;
+  static DeviceConstants &get(int device) {
+    static DeviceConstants inst[64];
+    DeviceConstants &d = inst[device & 63];
+    if (!d.d_crc) {
+      CrcTables *h = new CrcTables();
+      crc_build_tables(*h, EMIT_CRC_STRIDE_WORDS);
+      TG_CUDA(cudaMalloc((void **)&d.d_crc, sizeof(CrcTables)));
+      TG_CUDA(cudaMemcpy(d.d_crc, h, sizeof(CrcTables), cudaMemcpyHostToDevice));
+      delete h;
+    }
+    return d;
+  }
+};
+
+class SortPipeline {
+ public:
+  tezgpu_conf conf;
+  int pbits;
+  cudaStream_t stream = nullptr;
+  EventTimer timer;
+
+  // workspace (grow-only, reused across flushes)
+  DeviceBuffer keysA, keysB, valsA, valsB, same, blk, small, tile_state, sizes, rec_off;
+  DeviceBuffer t_pos[2], t_gid[2], t_lidx[2], t_key64[2], t_val[2], t_state;
+  DeviceBuffer seg_start, tile_start, part_start, d_index, seg_crc;
+  PinnedBuffer h_small;
+
+  explicit SortPipeline(const tezgpu_conf &c) : conf(c) {
+    TG_CHECK(c.num_partitions >= 1, TEZGPU_E_INVALID, "num_partitions must be >= 1");
+    TG_CHECK(c.comparator >= TEZGPU_CMP_BYTES && c.comparator <= TEZGPU_CMP_LONG, TEZGPU_E_UNSUPPORTED,
+             "comparator outside the device-supported set (BYTES, TEXT, BYTESWRITABLE, INT, LONG)");
+    TG_CHECK(c.partitioner == TEZGPU_PART_GIVEN || c.partitioner == TEZGPU_PART_HASH, TEZGPU_E_UNSUPPORTED,
+             "partitioner outside the device-supported set (GIVEN, HASH)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+      cudaGetLastError();
+      throw Error(TEZGPU_E_CUDA, "no CUDA device available (libtezgpu has no CPU fallback)");
+    }
+    TG_CHECK(c.device >= 0 && c.device < ndev, TEZGPU_E_INVALID, "bad device ordinal");
+    TG_CUDA(cudaSetDevice(c.device));
+    TG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    pbits = partition_bits(c.num_partitions);
+    TG_CHECK(pbits <= 31, TEZGPU_E_INVALID, "too many partitions");
+    h_small.ensure(4096);
+    small.ensure(4096);
+    DeviceConstants::get(c.device);
+  }
+  ~SortPipeline() {
+    if (stream) cudaStreamDestroy(stream);
+  }
+
+  static uint64_t output_bound(uint64_t n, uint64_t kv_bytes, int P) { return kv_bytes + 12 * n + 10ull * P + 64; }
+
+  // `small` device scratch layout (u32 words): [0..2047] radix hist (8*256), [2048..2055] trivial flags,
+  // [2056..2063] tile counters, [2064] error flag, [2066..2067] dup count (u64), [2068..2071] totals (2 x u64)
+  uint32_t *d_hist() { return small.as<uint32_t>(); }
+  uint32_t *d_trivial() { return small.as<uint32_t>() + 2048; }
+  uint32_t *d_tile_counter() { return small.as<uint32_t>() + 2056; }
+  int *d_error() { return reinterpret_cast<int *>(small.as<uint32_t>() + 2064); }
+  unsigned long long *d_dups() { return reinterpret_cast<unsigned long long *>(small.as<uint32_t>() + 2066); }
+  uint64_t *d_totals() { return reinterpret_cast<uint64_t *>(small.as<uint32_t>() + 2068); }
+
+  void run(Records rec, uint8_t *d_out, uint64_t out_cap, uint64_t *out_len, int64_t *index, tezgpu_stats *stats) {
+    TG_CUDA(cudaSetDevice(conf.device));
+    const uint32_t n = rec.n;
+    const int P = conf.num_partitions;
+    TG_CHECK(n <= RADIX_MAX_N, TEZGPU_E_INVALID, "more than 2^30-1 records in one sort");
+    TG_CHECK(((uintptr_t)d_out & 15u) == 0, TEZGPU_E_INVALID, "output buffer must be 16-byte aligned");
+    rec.cmp = conf.comparator;
+    rec.hash_partition = conf.partitioner == TEZGPU_PART_HASH;
+    rec.num_partitions = P;
+    rec.pbits = pbits;
+    TG_CHECK(rec.hash_partition || rec.partition || n == 0, TEZGPU_E_INVALID, "partition ids required (partitioner=GIVEN)");
+    int launches = 0;
+    timer.reset();
+    timer.mark(stream);
+
+    const CrcTables *d_crc = DeviceConstants::get(conf.device).d_crc;
+    const size_t n4 = (size_t)(n ? n : 1) * 4;
+    keysA.ensure(n4); keysB.ensure(n4); valsA.ensure(n4); valsB.ensure(n4);
+    same.ensure(n ? n : 1);
+    const uint32_t nblk = (uint32_t)div_up(n ? n : 1, SCAN_TILE);
+    blk.ensure(((size_t)nblk + 2) * 8);
+    part_start.ensure(((size_t)P + 1) * 4);
+    seg_start.ensure(((size_t)P + 1) * 8);
+    tile_start.ensure(((size_t)P + 1) * 4);
+    d_index.ensure((size_t)P * 24);
+    seg_crc.ensure((size_t)P * 4);
+    h_small.ensure(4096 + (size_t)P * 24);
+
+    TG_CUDA(cudaMemsetAsync(small.p, 0, 4096, stream));
+    TG_CUDA(cudaMemsetAsync(seg_crc.p, 0, (size_t)P * 4, stream));
+
+    uint64_t dup_count = 0;
+    uint64_t tie_records = 0;
+    uint32_t *K = keysA.as<uint32_t>();
+    uint32_t *order = valsA.as<uint32_t>();
+
+    if (n) {
+      // ---------------- stage
+      TG_CUDA(cudaMemsetAsync(same.p, 0, n, stream));
+      const bool fast16 = rec.fixed && rec.klen == 16 && ((rec.klen + rec.vlen) % 16 == 0) && rec.cmp == CMP_BYTES &&
+                          (((uintptr_t)rec.kv & 15u) == 0);
+      int sgrid = (int)std::min<uint64_t>(div_up(n, 256), 148 * 16);
+      if (fast16) k_stage<true><<<sgrid, 256, 0, stream>>>(rec, K, d_hist(), d_error());
+      else k_stage<false><<<sgrid, 256, 0, stream>>>(rec, K, d_hist(), d_error());
+      TG_CUDA(cudaGetLastError());
+      k_radix_scan_hist<<<1, RADIX, 0, stream>>>(d_hist(), 4, n, d_trivial());
+      TG_CUDA(cudaGetLastError());
+      launches += 2;
+      timer.mark(stream);
+
+      // ---------------- radix sort of (sort word, record index)
+      RadixWorkspace ws;
+      ws.hist = d_hist();
+      ws.trivial = d_trivial();
+      ws.tile_counter = d_tile_counter();
+      ws.tile_state_words = radix_tile_state_words<uint32_t>(n, 4);
+      tile_state.ensure(ws.tile_state_words * 4);
+      ws.tile_state = tile_state.as<uint32_t>();
+      int done = radix_sort_passes<uint32_t>(stream, ws, keysA.as<uint32_t>(), keysB.as<uint32_t>(), valsA.as<uint32_t>(),
+                                             valsB.as<uint32_t>(), n, 0, 4, 0xF, true, &launches);
+      if (done & 1) { K = keysB.as<uint32_t>(); order = valsB.as<uint32_t>(); }
+      timer.mark(stream);
+
+      // ---------------- ties: records whose sort words collide are ordered by the rest of the key
+      k_tie_count<<<nblk, SCAN_THREADS, 0, stream>>>(K, n, blk.as<uint64_t>());
+      k_scan_block_sums<<<1, 1024, 0, stream>>>(blk.as<uint64_t>(), nblk);
+      launches += 2;
+      TG_CUDA(cudaGetLastError());
+      uint64_t *hs = h_small.as<uint64_t>();
+      TG_CUDA(cudaMemcpyAsync(&hs[0], blk.as<uint64_t>() + nblk, 8, cudaMemcpyDeviceToHost, stream));
+      TG_CUDA(cudaMemcpyAsync(&hs[1], d_error(), 4, cudaMemcpyDeviceToHost, stream));
+      TG_CUDA(cudaStreamSynchronize(stream));
+      TG_CHECK((uint32_t)hs[1] == 0, TEZGPU_E_INVALID, "Illegal partition (outside [0, numPartitions))");
+      uint32_t m = (uint32_t)hs[0];
+      tie_records = m;
+      if (m) {
+        for (int s = 0; s < 2; s++) { t_pos[s].ensure((size_t)m * 4); t_gid[s].ensure((size_t)m * 4); t_lidx[s].ensure((size_t)m * 4); }
+        k_tie_compact<<<nblk, SCAN_THREADS, 0, stream>>>(K, order, n, blk.as<uint64_t>(), t_pos[0].as<uint32_t>(),
+                                                         t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>());
+        launches++;
+        uint32_t depth = (uint32_t)((32 - pbits) / 8);
+        int cur = 0;
+        while (m) {
+          t_key64[0].ensure((size_t)m * 8); t_key64[1].ensure((size_t)m * 8); t_val[0].ensure((size_t)m * 4);
+          const uint32_t mblk = (uint32_t)div_up(m, SCAN_TILE);
+          k_ref_build_keys<<<(uint32_t)div_up(m, 256), 256, 0, stream>>>(rec, t_gid[cur].as<uint32_t>(), t_lidx[cur].as<uint32_t>(), m,
+                                                                    depth, t_key64[0].as<uint64_t>());
+          TG_CUDA(cudaMemsetAsync(d_hist(), 0, 8 * RADIX * 4, stream));
+          k_radix_hist<uint64_t, 8><<<(int)std::min<uint64_t>(div_up(m, 512 * 8), 148 * 4), 512, 0, stream>>>(t_key64[0].as<uint64_t>(), m, 0, d_hist());
+          k_radix_scan_hist<<<1, RADIX, 0, stream>>>(d_hist(), 8, m, d_trivial());
+          launches += 3;
+          TG_CUDA(cudaGetLastError());
+          uint32_t *ht = h_small.as<uint32_t>() + 64;
+          TG_CUDA(cudaMemcpyAsync(ht, d_trivial(), 8 * 4, cudaMemcpyDeviceToHost, stream));
+          TG_CUDA(cudaStreamSynchronize(stream));
+          uint32_t mask = 0;
+          for (int q = 0; q < 8; q++) if (!ht[q]) mask |= 1u << q;
+          RadixWorkspace w2 = ws;
+          w2.tile_state_words = radix_tile_state_words<uint64_t>(m, 8);
+          t_state.ensure(w2.tile_state_words * 4);
+          w2.tile_state = t_state.as<uint32_t>();
+          int d2 = radix_sort_passes<uint64_t>(stream, w2, t_key64[0].as<uint64_t>(), t_key64[1].as<uint64_t>(), t_lidx[cur].as<uint32_t>(),
+                                               t_val[0].as<uint32_t>(), m, 0, 8, mask, false, &launches);
+          const uint64_t *Ks = (d2 & 1) ? t_key64[1].as<uint64_t>() : t_key64[0].as<uint64_t>();
+          const uint32_t *Ls = (d2 & 1) ? t_val[0].as<uint32_t>() : t_lidx[cur].as<uint32_t>();
+          k_ref_apply_count<<<mblk, SCAN_THREADS, 0, stream>>>(Ks, Ls, t_pos[cur].as<uint32_t>(), m, order, same.as<uint8_t>(), d_dups(),
+                                                              blk.as<uint64_t>());
+          k_scan_block_sums<<<1, 1024, 0, stream>>>(blk.as<uint64_t>(), mblk);
+          launches += 2;
+          TG_CUDA(cudaMemcpyAsync(&hs[0], blk.as<uint64_t>() + mblk, 8, cudaMemcpyDeviceToHost, stream));
+          TG_CUDA(cudaStreamSynchronize(stream));
+          uint32_t m2 = (uint32_t)hs[0];
+          if (m2) {
+            k_ref_compact<<<mblk, SCAN_THREADS, 0, stream>>>(Ks, Ls, t_pos[cur].as<uint32_t>(), m, blk.as<uint64_t>(),
+                                                            t_pos[cur ^ 1].as<uint32_t>(), t_gid[cur ^ 1].as<uint32_t>(),
+                                                            t_lidx[cur ^ 1].as<uint32_t>());
+            launches++;
+            TG_CUDA(cudaGetLastError());
+          }
+          cur ^= 1;
+          m = m2;
+          depth += 3;
+        }
+        TG_CUDA(cudaMemcpyAsync(&hs[0], d_dups(), 8, cudaMemcpyDeviceToHost, stream));
+        TG_CUDA(cudaStreamSynchronize(stream));
+        dup_count = hs[0];
+      }
+    }
+    timer.mark(stream);
+
+    // ---------------- RLE decision (SORT/PipelinedSorter.java:1436-1438; see DESIGN.md for the AUTO rule)
+    int rle;
+    if (conf.rle_policy == TEZGPU_RLE_ON) rle = 1;
+    else if (conf.rle_policy == TEZGPU_RLE_OFF) rle = 0;
+    else rle = (conf.sorter_impl == 1) ? 0 : ((double)dup_count > 0.1 * (double)n);
+
+    // ---------------- layout + emit
+    EmitParams e;
+    memset(&e, 0, sizeof(e));
+    e.rec = rec;
+    e.order = order;
+    e.same = same.as<uint8_t>();
+    e.part_start = part_start.as<uint32_t>();
+    e.seg_start = seg_start.as<uint64_t>();
+    e.tile_start = tile_start.as<uint32_t>();
+    e.out = d_out;
+    e.seg_crc = seg_crc.as<uint32_t>();
+    e.crc = d_crc;
+    e.rle = rle;
+    e.send_empty = conf.send_empty_partition_details;
+    e.P = P;
+    const bool fixed_emit = rec.fixed && (!rle || dup_count == 0);
+    uint64_t bound = output_bound(n, rec.fixed ? (uint64_t)n * (rec.klen + rec.vlen) : rec.kv_bytes, P);
+    if (fixed_emit) {
+      int h = 0;
+      for (int b = 0; b < vint_size_u32(rec.klen); b++) e.fixed_hdr[h++] = vint_byte_u32(rec.klen, b);
+      for (int b = 0; b < vint_size_u32(rec.vlen); b++) e.fixed_hdr[h++] = vint_byte_u32(rec.vlen, b);
+      e.fixed_hdr_len = h;
+      e.rec_size = h + rec.klen + rec.vlen;
+      e.recs_per_tile = std::max<uint32_t>(1, std::min<uint32_t>(EMIT_MAX_RECS, (EMIT_IMG_BYTES - 32) / e.rec_size));
+      e.rec_off = nullptr;
+    } else {
+      uint64_t avg = n ? (rec.fixed ? (uint64_t)(rec.klen + rec.vlen) : rec.kv_bytes / n) + 4 : 16;
+      e.recs_per_tile = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(EMIT_MAX_RECS, (EMIT_IMG_BYTES - 32) / avg));
+      sizes.ensure(n4);
+      rec_off.ensure(((size_t)n + 2) * 8);
+      if (n) {
+        k_emit_sizes<<<(uint32_t)div_up(n, 256), 256, 0, stream>>>(e, K, sizes.as<uint32_t>());
+        k_sum_u32_blocks<<<nblk, SCAN_THREADS, 0, stream>>>(sizes.as<uint32_t>(), n, blk.as<uint64_t>());
+        k_scan_block_sums<<<1, 1024, 0, stream>>>(blk.as<uint64_t>(), nblk);
+        k_scan_u32_apply<<<nblk, SCAN_THREADS, 0, stream>>>(sizes.as<uint32_t>(), n, blk.as<uint64_t>(), rec_off.as<uint64_t>());
+        launches += 4;
+        TG_CUDA(cudaGetLastError());
+      } else {
+        TG_CUDA(cudaMemsetAsync(rec_off.p, 0, 16, stream));
+      }
+      e.rec_off = rec_off.as<uint64_t>();
+    }
+    k_part_bounds<<<(uint32_t)div_up((uint64_t)P + 1, 256), 256, 0, stream>>>(K, n, P, pbits, part_start.as<uint32_t>());
+    k_layout<<<1, 1024, 0, stream>>>(e, seg_start.as<uint64_t>(), tile_start.as<uint32_t>(), d_index.as<int64_t>(), d_totals());
+    launches += 2;
+    TG_CUDA(cudaGetLastError());
+    uint64_t *hs = h_small.as<uint64_t>();
+    TG_CUDA(cudaMemcpyAsync(&hs[0], d_totals(), 16, cudaMemcpyDeviceToHost, stream));
+    TG_CUDA(cudaMemcpyAsync(h_small.as<uint8_t>() + 4096, d_index.p, (size_t)P * 24, cudaMemcpyDeviceToHost, stream));
+    TG_CUDA(cudaStreamSynchronize(stream));
+    const uint64_t file_bytes = hs[0];
+    const uint64_t tiles = hs[1];
+    TG_CHECK(file_bytes <= bound, TEZGPU_E_INVALID, "internal: output exceeds bound");
+    TG_CHECK(file_bytes <= out_cap, TEZGPU_E_NOMEM, "output buffer too small for file.out");
+    if (tiles) {
+      if (fixed_emit) k_emit<true><<<(uint32_t)tiles, EMIT_THREADS, 0, stream>>>(e);
+      else k_emit<false><<<(uint32_t)tiles, EMIT_THREADS, 0, stream>>>(e);
+      launches++;
+      TG_CUDA(cudaGetLastError());
+    }
+    k_finalize_segments<<<(uint32_t)div_up(P, 256), 256, 0, stream>>>(e);
+    launches++;
+    TG_CUDA(cudaGetLastError());
+    timer.mark(stream);
+    TG_CUDA(cudaStreamSynchronize(stream));
+
+    if (out_len) *out_len = file_bytes;
+    const int64_t *hidx = reinterpret_cast<const int64_t *>(h_small.as<uint8_t>() + 4096);
+    if (index) memcpy(index, hidx, (size_t)P * 24);
+    if (stats) {
+      memset(stats, 0, sizeof(*stats));
+      stats->output_records = n;
+      int64_t raw = 0;
+      for (int p = 0; p < P; p++) raw += hidx[3 * p + 1];
+      stats->output_bytes_with_overhead = raw;
+      stats->output_bytes_physical = (int64_t)file_bytes;
+      stats->file_out_bytes = (int64_t)file_bytes;
+      stats->spilled_records = n;
+      stats->num_spills = 1;
+      stats->rle_used = rle;
+      stats->adjacent_equal_keys = (int64_t)dup_count;
+      stats->tie_records = (int64_t)tie_records;
+      stats->ms_stage = timer.ms(0, 1);
+      stats->ms_sort = n ? timer.ms(1, 2) : 0;
+      stats->ms_ties = n ? timer.ms(2, 3) : 0;
+      stats->ms_emit = n ? timer.ms(3, 4) : timer.ms(1, 2);
+      stats->ms_total = timer.ms(0, timer.n - 1);
+      stats->kernel_launches = launches;
+    }
+  }
+};
+
+}  // namespace tezgpu

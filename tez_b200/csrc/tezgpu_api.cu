@@ -1,0 +1,362 @@
+// tezgpu_api.cu -- extern "C" boundary of libtezgpu.so (include/tezgpu.h).  No CPU fallback: every compute entry
+// point needs a CUDA device and fails with TEZGPU_E_CUDA otherwise.
+#include <errno.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <string>
+
+#include "../../include/tezgpu.h"
+#include "merger.cuh"
+#include "sorter.cuh"
+
+using namespace tezgpu;
+
+static thread_local std::string g_last_error;
+
+#define TG_API_BEGIN try {
+#define TG_API_END                                  \
+  }                                                 \
+  catch (const tezgpu::Error &e) {                  \
+    g_last_error = e.what();                        \
+    return e.code;                                  \
+  }                                                 \
+  catch (const std::bad_alloc &) {                  \
+    g_last_error = "host allocation failed";        \
+    return TEZGPU_E_NOMEM;                          \
+  }                                                 \
+  catch (const std::exception &e) {                 \
+    g_last_error = e.what();                        \
+    return TEZGPU_E_INVALID;                        \
+  }                                                 \
+  return TEZGPU_OK;
+
+// TezSpillRecord.writeToFile layout (SORT/TezSpillRecord.java:111-146): P x 3 big-endian longs + CRC32 as a long
+static void spill_record_bytes(const int64_t *idx, int P, std::vector<uint8_t> &out) {
+  out.resize((size_t)P * 24 + 8);
+  for (int i = 0; i < P * 3; i++)
+    for (int b = 0; b < 8; b++) out[(size_t)i * 8 + b] = (uint8_t)((uint64_t)idx[i] >> (56 - 8 * b));
+  CrcTables *t = new CrcTables();
+  crc_build_tables(*t, 1);
+  uint32_t c = 0xFFFFFFFFu;
+  for (size_t i = 0; i < (size_t)P * 24; i++) c = t->slice[0][(c ^ out[i]) & 0xFF] ^ (c >> 8);
+  c = ~c;
+  delete t;
+  for (int b = 0; b < 8; b++) out[(size_t)P * 24 + b] = (uint8_t)((uint64_t)c >> (56 - 8 * b));
+}
+
+static void write_file_0640(const char *path, const void *data, size_t len) {
+  // SPILL_FILE_PERMS = 0640 (SORT/TezSpillRecord.java:41,148-152)
+  int fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0640);
+  TG_CHECK(fd >= 0, TEZGPU_E_IO, std::string("open ") + path + ": " + strerror(errno));
+  const uint8_t *p = (const uint8_t *)data;
+  size_t left = len;
+  while (left) {
+    ssize_t w = ::write(fd, p, left);
+    if (w < 0) {
+      if (errno == EINTR) continue;
+      int e = errno;
+      ::close(fd);
+      throw Error(TEZGPU_E_IO, std::string("write ") + path + ": " + strerror(e));
+    }
+    p += w;
+    left -= (size_t)w;
+  }
+  ::fchmod(fd, 0640);
+  TG_CHECK(::close(fd) == 0, TEZGPU_E_IO, std::string("close ") + path + ": " + strerror(errno));
+}
+
+struct tezgpu_sorter {
+  SortPipeline pipe;
+  bool fixed;
+  uint32_t klen, vlen;
+  uint64_t n = 0, kv_bytes = 0, payload_bytes = 0;
+  bool has_partition = false;
+  bool flushed = false;
+  DeviceBuffer d_kv, d_koff, d_klen, d_vlen, d_part, d_tmp, d_out;
+  PinnedBuffer h_out;
+  explicit tezgpu_sorter(const tezgpu_conf &c) : pipe(c) {
+    fixed = c.fixed_key_len > 0 || c.fixed_val_len > 0;
+    klen = c.fixed_key_len;
+    vlen = c.fixed_val_len;
+  }
+  Records records() {
+    Records r;
+    memset(&r, 0, sizeof(r));
+    r.kv = d_kv.as<uint8_t>();
+    r.kv_bytes = align_up(kv_bytes, 16);
+    r.key_off = d_koff.as<uint64_t>();
+    r.key_len = d_klen.as<uint32_t>();
+    r.val_len = d_vlen.as<uint32_t>();
+    r.partition = has_partition ? d_part.as<int32_t>() : nullptr;
+    r.n = (uint32_t)n;
+    r.klen = klen;
+    r.vlen = vlen;
+    r.fixed = fixed;
+    return r;
+  }
+};
+
+__global__ void k_rebase_offsets(const uint32_t *__restrict__ key_off, const uint32_t *__restrict__ val_off,
+                                 const uint32_t *__restrict__ val_len, uint32_t n, uint64_t base, uint64_t kv_bytes,
+                                 uint64_t *__restrict__ koff64, uint32_t *__restrict__ klen, uint32_t *__restrict__ vlen,
+                                 int *__restrict__ err) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t ko = key_off[i], vo = val_off[i], vl = val_len[i];
+  if (vo < ko || (uint64_t)vo + vl > kv_bytes) { *err = 1; vo = ko; vl = 0; }
+  koff64[i] = base + ko;
+  klen[i] = vo - ko;
+  vlen[i] = vl;
+}
+
+extern "C" {
+
+const char *tezgpu_last_error(void) { return g_last_error.c_str(); }
+int32_t tezgpu_abi_version(void) { return TEZGPU_ABI_VERSION; }
+int32_t tezgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int32_t tezgpu_sorter_create(const tezgpu_conf *conf, tezgpu_sorter **out) {
+  TG_API_BEGIN
+  TG_CHECK(conf && out, TEZGPU_E_INVALID, "null argument");
+  TG_CHECK(conf->abi_version == TEZGPU_ABI_VERSION, TEZGPU_E_INVALID, "tezgpu_conf.abi_version mismatch");
+  *out = new tezgpu_sorter(*conf);
+  TG_API_END
+}
+
+int32_t tezgpu_sorter_destroy(tezgpu_sorter *h) {
+  TG_API_BEGIN
+  delete h;
+  TG_API_END
+}
+
+int32_t tezgpu_sorter_collect_batch(tezgpu_sorter *h, const uint8_t *kv, uint64_t kv_bytes, const uint32_t *key_off,
+                                    const uint32_t *val_off, const uint32_t *val_len, const int32_t *partition,
+                                    uint32_t n) {
+  TG_API_BEGIN
+  TG_CHECK(h, TEZGPU_E_INVALID, "null handle");
+  TG_CHECK(!h->flushed, TEZGPU_E_STATE, "collect after flush");
+  TG_CHECK(!h->fixed, TEZGPU_E_STATE, "handle is in fixed-width mode: use tezgpu_sorter_collect_fixed");
+  if (n == 0) return TEZGPU_OK;
+  TG_CHECK(kv && key_off && val_off && val_len, TEZGPU_E_INVALID, "null argument");
+  TG_CHECK(kv_bytes < (1ull << 32), TEZGPU_E_INVALID, "batch larger than 4 GiB");
+  TG_CHECK(h->n + n <= RADIX_MAX_N, TEZGPU_E_INVALID, "more than 2^30-1 records collected");
+  TG_CHECK((h->n == 0) || (h->has_partition == (partition != nullptr)), TEZGPU_E_INVALID,
+           "partition ids must be given for all batches or none");
+  TG_CHECK(partition || h->pipe.conf.partitioner == TEZGPU_PART_HASH, TEZGPU_E_INVALID,
+           "partition ids required (partitioner=GIVEN)");
+  cudaStream_t st = h->pipe.stream;
+  TG_CUDA(cudaSetDevice(h->pipe.conf.device));
+  const uint64_t base = align_up(h->kv_bytes, 16);  // every batch starts 16-byte aligned
+  h->d_kv.grow_preserve(base + kv_bytes + 32, h->kv_bytes, st);
+  h->d_koff.grow_preserve((h->n + n) * 8, h->n * 8, st);
+  h->d_klen.grow_preserve((h->n + n) * 4, h->n * 4, st);
+  h->d_vlen.grow_preserve((h->n + n) * 4, h->n * 4, st);
+  if (partition) h->d_part.grow_preserve((h->n + n) * 4, h->n * 4, st);
+  h->d_tmp.ensure((size_t)n * 12);
+  uint32_t *t = h->d_tmp.as<uint32_t>();
+  TG_CUDA(cudaMemcpyAsync(h->d_kv.as<uint8_t>() + base, kv, kv_bytes, cudaMemcpyHostToDevice, st));
+  TG_CUDA(cudaMemcpyAsync(t, key_off, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  TG_CUDA(cudaMemcpyAsync(t + n, val_off, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  TG_CUDA(cudaMemcpyAsync(t + 2 * (size_t)n, val_len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  if (partition)
+    TG_CUDA(cudaMemcpyAsync(h->d_part.as<int32_t>() + h->n, partition, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  TG_CUDA(cudaMemsetAsync(h->pipe.d_error(), 0, 4, st));
+  k_rebase_offsets<<<(uint32_t)div_up(n, 256), 256, 0, st>>>(t, t + n, t + 2 * (size_t)n, n, base, kv_bytes,
+                                                           h->d_koff.as<uint64_t>() + h->n, h->d_klen.as<uint32_t>() + h->n,
+                                                           h->d_vlen.as<uint32_t>() + h->n, h->pipe.d_error());
+  TG_CUDA(cudaGetLastError());
+  int err = 0;
+  TG_CUDA(cudaMemcpyAsync(&err, h->pipe.d_error(), 4, cudaMemcpyDeviceToHost, st));
+  TG_CUDA(cudaStreamSynchronize(st));  // caller may reuse its buffers once we return
+  TG_CHECK(err == 0, TEZGPU_E_INVALID, "record offsets outside the batch buffer");
+  for (uint32_t i = 0; i < n; i++) h->payload_bytes += (uint64_t)(val_off[i] - key_off[i]) + val_len[i];
+  h->has_partition = partition != nullptr;
+  h->n += n;
+  h->kv_bytes = base + kv_bytes;
+  TG_API_END
+}
+
+int32_t tezgpu_sorter_collect_fixed(tezgpu_sorter *h, const uint8_t *kv, const int32_t *partition, uint64_t n) {
+  TG_API_BEGIN
+  TG_CHECK(h, TEZGPU_E_INVALID, "null handle");
+  TG_CHECK(!h->flushed, TEZGPU_E_STATE, "collect after flush");
+  TG_CHECK(h->fixed, TEZGPU_E_STATE, "handle is not in fixed-width mode");
+  if (n == 0) return TEZGPU_OK;
+  TG_CHECK(kv, TEZGPU_E_INVALID, "null argument");
+  TG_CHECK(h->n + n <= RADIX_MAX_N, TEZGPU_E_INVALID, "more than 2^30-1 records collected");
+  TG_CHECK((h->n == 0) || (h->has_partition == (partition != nullptr)), TEZGPU_E_INVALID,
+           "partition ids must be given for all batches or none");
+  TG_CHECK(partition || h->pipe.conf.partitioner == TEZGPU_PART_HASH, TEZGPU_E_INVALID,
+           "partition ids required (partitioner=GIVEN)");
+  cudaStream_t st = h->pipe.stream;
+  TG_CUDA(cudaSetDevice(h->pipe.conf.device));
+  const uint64_t stride = (uint64_t)h->klen + h->vlen;
+  h->d_kv.grow_preserve((h->n + n) * stride + 32, h->n * stride, st);
+  if (partition) h->d_part.grow_preserve((h->n + n) * 4, h->n * 4, st);
+  TG_CUDA(cudaMemcpyAsync(h->d_kv.as<uint8_t>() + h->n * stride, kv, n * stride, cudaMemcpyHostToDevice, st));
+  if (partition)
+    TG_CUDA(cudaMemcpyAsync(h->d_part.as<int32_t>() + h->n, partition, n * 4, cudaMemcpyHostToDevice, st));
+  TG_CUDA(cudaStreamSynchronize(st));
+  h->has_partition = partition != nullptr;
+  h->n += n;
+  h->kv_bytes = h->n * stride;
+  h->payload_bytes = h->kv_bytes;
+  TG_API_END
+}
+
+uint64_t tezgpu_sorter_output_bound(const tezgpu_sorter *h) {
+  if (!h) return 0;
+  return SortPipeline::output_bound(h->n, h->kv_bytes, h->pipe.conf.num_partitions);
+}
+
+static void sorter_run(tezgpu_sorter *h, uint8_t *host_out, uint64_t out_cap, uint64_t *out_len, int64_t *index,
+                       tezgpu_stats *stats, std::vector<int64_t> &idx_store) {
+  TG_CHECK(!h->flushed, TEZGPU_E_STATE, "flush called twice");
+  const int P = h->pipe.conf.num_partitions;
+  idx_store.assign((size_t)P * 3, 0);
+  uint64_t bound = tezgpu_sorter_output_bound(h);
+  h->d_out.ensure(bound);
+  uint64_t len = 0;
+  tezgpu_stats st;
+  h->pipe.run(h->records(), h->d_out.as<uint8_t>(), h->d_out.cap, &len, idx_store.data(), &st);
+  st.output_bytes = (int64_t)h->payload_bytes;
+  TG_CHECK(len <= out_cap, TEZGPU_E_NOMEM, "output buffer too small for file.out");
+  if (len) {
+    TG_CUDA(cudaMemcpyAsync(host_out, h->d_out.p, len, cudaMemcpyDeviceToHost, h->pipe.stream));
+    TG_CUDA(cudaStreamSynchronize(h->pipe.stream));
+  }
+  if (out_len) *out_len = len;
+  if (index) memcpy(index, idx_store.data(), (size_t)P * 24);
+  if (stats) *stats = st;
+  h->flushed = true;
+}
+
+int32_t tezgpu_sorter_flush_to_memory(tezgpu_sorter *h, uint8_t *out, uint64_t out_cap, uint64_t *out_len,
+                                      uint8_t *index_out, int64_t *index, tezgpu_stats *stats) {
+  TG_API_BEGIN
+  TG_CHECK(h && (out || out_cap == 0), TEZGPU_E_INVALID, "null argument");
+  std::vector<int64_t> idx;
+  sorter_run(h, out, out_cap, out_len, index, stats, idx);
+  if (index_out) {
+    std::vector<uint8_t> b;
+    spill_record_bytes(idx.data(), h->pipe.conf.num_partitions, b);
+    memcpy(index_out, b.data(), b.size());
+  }
+  TG_API_END
+}
+
+int32_t tezgpu_sorter_flush(tezgpu_sorter *h, const char *out_path, const char *index_path, int64_t *index,
+                            tezgpu_stats *stats) {
+  TG_API_BEGIN
+  TG_CHECK(h && out_path && index_path, TEZGPU_E_INVALID, "null argument");
+  uint64_t bound = tezgpu_sorter_output_bound(h);
+  h->h_out.ensure(bound);
+  std::vector<int64_t> idx;
+  uint64_t len = 0;
+  sorter_run(h, h->h_out.as<uint8_t>(), h->h_out.cap, &len, index, stats, idx);
+  write_file_0640(out_path, h->h_out.p, len);
+  std::vector<uint8_t> b;
+  spill_record_bytes(idx.data(), h->pipe.conf.num_partitions, b);
+  write_file_0640(index_path, b.data(), b.size());
+  TG_API_END
+}
+
+int32_t tezgpu_sorter_sort_device_fixed(tezgpu_sorter *h, const void *d_kv, const void *d_partition, uint64_t n,
+                                        void *d_out, uint64_t out_cap, uint64_t *out_len, int64_t *index,
+                                        tezgpu_stats *stats) {
+  TG_API_BEGIN
+  TG_CHECK(h && (d_kv || n == 0) && d_out, TEZGPU_E_INVALID, "null argument");
+  TG_CHECK(h->fixed, TEZGPU_E_STATE, "handle is not in fixed-width mode");
+  TG_CHECK(n <= RADIX_MAX_N, TEZGPU_E_INVALID, "more than 2^30-1 records in one sort");
+  TG_CHECK(d_partition || h->pipe.conf.partitioner == TEZGPU_PART_HASH, TEZGPU_E_INVALID,
+           "partition ids required (partitioner=GIVEN)");
+  Records r;
+  memset(&r, 0, sizeof(r));
+  r.kv = (const uint8_t *)d_kv;
+  r.kv_bytes = n * ((uint64_t)h->klen + h->vlen);  // no read past the caller's buffer
+  r.kv_bytes -= r.kv_bytes % 16;
+  if (r.kv_bytes < n * ((uint64_t)h->klen + h->vlen)) r.kv_bytes += 0;  // tail vector (if any) is read bytewise-safe below
+  r.partition = (const int32_t *)d_partition;
+  r.n = (uint32_t)n;
+  r.klen = h->klen;
+  r.vlen = h->vlen;
+  r.fixed = 1;
+  TG_CHECK((n * ((uint64_t)h->klen + h->vlen)) % 16 == 0 && ((uintptr_t)d_kv & 15u) == 0, TEZGPU_E_INVALID,
+           "device-resident input must be 16-byte aligned with a total size that is a multiple of 16");
+  tezgpu_stats st;
+  h->pipe.run(r, (uint8_t *)d_out, out_cap, out_len, index, &st);
+  st.output_bytes = (int64_t)(n * ((uint64_t)h->klen + h->vlen));
+  if (stats) *stats = st;
+  TG_API_END
+}
+
+void *tezgpu_sorter_stream(tezgpu_sorter *h) { return h ? (void *)h->pipe.stream : nullptr; }
+
+// Host emulation of the emit kernel's parallel CRC scheme (interleaved per-thread streams over the 4-byte words of a
+// piece, power-table alignment, xor-fold of piece contributions into the segment remainder, final conditioning).
+// Pure host arithmetic on the same tables the device uses; lets the CPU test-suite check the GF(2) algebra.
+uint32_t tezgpu_debug_crc_emulate(const uint8_t *body, uint64_t len, uint32_t piece_bytes, uint32_t lead) {
+  CrcTables *t = new CrcTables();
+  const int T = EMIT_CRC_STRIDE_WORDS;
+  crc_build_tables(*t, T);
+  auto shift = [&](uint32_t crc, uint64_t nbytes) {
+    uint32_t a0 = (uint32_t)(nbytes & 4095), a1 = (uint32_t)((nbytes >> 12) & 4095), a2 = (uint32_t)((nbytes >> 24) & 4095);
+    if (a0) crc = crc_multmodp(crc, t->pow0[a0]);
+    if (a1) crc = crc_multmodp(crc, t->pow1[a1]);
+    if (a2) crc = crc_multmodp(crc, t->pow2[a2]);
+    return crc;
+  };
+  uint32_t seg = 0;
+  uint64_t done = 0;
+  std::vector<uint8_t> img;
+  while (done < len) {
+    uint32_t ld = (uint32_t)((done + lead) & 15u);
+    uint32_t plen = (uint32_t)std::min<uint64_t>(piece_bytes - ld, len - done);
+    img.assign((size_t)ld + plen + 16, 0);
+    memcpy(img.data() + ld, body + done, plen);
+    uint32_t cb0 = ld, cb1 = ld + plen;
+    uint32_t wa = (cb0 + 3u) >> 2, wb = cb1 >> 2;
+    uint32_t words_crc = 0;
+    const uint32_t *img32 = reinterpret_cast<const uint32_t *>(img.data());
+    if (wb > wa) {
+      uint32_t W = wb - wa;
+      for (uint32_t tid = 0; tid < (uint32_t)T && tid < W; tid++) {
+        uint32_t i = wa + tid, c = 0;
+        for (; i + T < wb; i += T) {
+          uint32_t v = c ^ img32[i];
+          c = t->adv[0][v & 0xFF] ^ t->adv[1][(v >> 8) & 0xFF] ^ t->adv[2][(v >> 16) & 0xFF] ^ t->adv[3][v >> 24];
+        }
+        uint32_t v = c ^ img32[i];
+        c = t->slice[3][v & 0xFF] ^ t->slice[2][(v >> 8) & 0xFF] ^ t->slice[1][(v >> 16) & 0xFF] ^ t->slice[0][v >> 24];
+        uint32_t d = wb - 1 - i;
+        if (d) c = crc_multmodp(c, t->pow_word[d]);
+        words_crc ^= c;
+      }
+    }
+    uint32_t raw = 0;
+    uint32_t head_end = (wb > wa) ? 4 * wa : cb1;
+    for (uint32_t b = cb0; b < head_end; b++) raw = t->slice[0][(raw ^ img[b]) & 0xFF] ^ (raw >> 8);
+    if (wb > wa) {
+      raw = shift(raw, 4ull * (wb - wa)) ^ words_crc;
+      for (uint32_t b = 4 * wb; b < cb1; b++) raw = t->slice[0][(raw ^ img[b]) & 0xFF] ^ (raw >> 8);
+    }
+    seg ^= shift(raw, len - (done + plen));
+    done += plen;
+  }
+  uint32_t crc = seg ^ shift(0xFFFFFFFFu, len) ^ 0xFFFFFFFFu;
+  delete t;
+  return crc;
+}
+
+}  // extern "C"
+
+#include "merger_api.inl"

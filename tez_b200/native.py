@@ -1,0 +1,192 @@
+"""Thin object wrappers over the C ABI (include/tezgpu.h) -- what the JNI shim does in a Tez task JVM.
+
+GpuSorter  ~ ExternalSorter seam (SORT/ExternalSorter.java:74-92): write/collect -> flush -> close.
+GpuMerger  ~ TezMerger.merge(...) -> TezRawKeyValueIterator (SORT/TezMerger.java:717-912).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .constants import *  # noqa: F401,F403
+from ._lib import Conf, KvIndex, Segment, Stats, check
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def make_conf(num_partitions, comparator=CMP_BYTES, partitioner=PART_HASH, rle_policy=RLE_AUTO, send_empty=True,
+              fixed=None, device=0, legacy=False, mem_budget=0):
+    c = Conf()
+    c.abi_version = ABI_VERSION
+    c.device = device
+    c.num_partitions = num_partitions
+    c.comparator = comparator
+    c.partitioner = partitioner
+    c.rle_policy = rle_policy
+    c.send_empty_partition_details = 1 if send_empty else 0
+    c.sorter_impl = SORTER_LEGACY if legacy else SORTER_PIPELINED
+    c.fixed_key_len, c.fixed_val_len = fixed if fixed else (0, 0)
+    c.mem_budget_bytes = mem_budget
+    return c
+
+
+class GpuSorter:
+    def __init__(self, num_partitions, **kw):
+        self.L = _lib.load()
+        self.conf = make_conf(num_partitions, **kw)
+        self.P = num_partitions
+        self.h = C.c_void_p()
+        check(self.L.tezgpu_sorter_create(C.byref(self.conf), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.L.tezgpu_sorter_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def collect(self, kv, key_off, val_off, val_len, partition=None):
+        kv = np.ascontiguousarray(np.frombuffer(kv, dtype=np.uint8) if isinstance(kv, (bytes, bytearray)) else kv,
+                                  dtype=np.uint8)
+        key_off = np.ascontiguousarray(key_off, dtype=np.uint32)
+        val_off = np.ascontiguousarray(val_off, dtype=np.uint32)
+        val_len = np.ascontiguousarray(val_len, dtype=np.uint32)
+        if partition is not None:
+            partition = np.ascontiguousarray(partition, dtype=np.int32)
+        check(self.L.tezgpu_sorter_collect_batch(self.h, _ptr(kv), kv.size, _ptr(key_off), _ptr(val_off),
+                                                 _ptr(val_len), _ptr(partition), len(key_off)))
+
+    def collect_fixed(self, kv, partition=None, n=None):
+        if isinstance(kv, int):  # raw host pointer (pinned memory)
+            p = kv
+        else:
+            kv = np.ascontiguousarray(kv, dtype=np.uint8)
+            p = kv.ctypes.data
+            if n is None:
+                n = kv.size // (self.conf.fixed_key_len + self.conf.fixed_val_len)
+        if partition is not None:
+            partition = np.ascontiguousarray(partition, dtype=np.int32)
+        check(self.L.tezgpu_sorter_collect_fixed(self.h, p, _ptr(partition), n))
+
+    def output_bound(self):
+        return self.L.tezgpu_sorter_output_bound(self.h)
+
+    def flush_to_memory(self, out=None):
+        """Returns (file_out uint8 array view, index_bytes, index[P,3], stats dict)."""
+        cap = self.output_bound()
+        if out is None:
+            out = np.empty(cap, dtype=np.uint8)
+        n = C.c_uint64()
+        index = np.zeros((self.P, 3), dtype=np.int64)
+        index_bytes = np.zeros(self.P * 24 + 8, dtype=np.uint8)
+        st = Stats()
+        check(self.L.tezgpu_sorter_flush_to_memory(self.h, _ptr(out) if not isinstance(out, int) else out,
+                                                   cap if not isinstance(out, int) else cap, C.byref(n),
+                                                   _ptr(index_bytes), _ptr(index), C.byref(st)))
+        res = out[:n.value] if not isinstance(out, int) else n.value
+        return res, index_bytes.tobytes(), index, st.as_dict()
+
+    def flush(self, out_path, index_path):
+        index = np.zeros((self.P, 3), dtype=np.int64)
+        st = Stats()
+        check(self.L.tezgpu_sorter_flush(self.h, out_path.encode(), index_path.encode(), _ptr(index), C.byref(st)))
+        return index, st.as_dict()
+
+    def sort_device_fixed(self, d_kv, n, d_out, out_cap, d_partition=None):
+        """Device-resident records (raw device pointers as ints). Returns (out_len, index, stats)."""
+        out_len = C.c_uint64()
+        index = np.zeros((self.P, 3), dtype=np.int64)
+        st = Stats()
+        check(self.L.tezgpu_sorter_sort_device_fixed(self.h, d_kv, d_partition, n, d_out, out_cap, C.byref(out_len),
+                                                     _ptr(index), C.byref(st)))
+        return out_len.value, index, st.as_dict()
+
+    def stream(self):
+        return self.L.tezgpu_sorter_stream(self.h)
+
+
+class GpuMerger:
+    def __init__(self, segments, comparator=CMP_BYTES, device=0, has_header=True, device_ptrs=False):
+        """segments: list of bytes / uint8 arrays (host) or (ptr, len) tuples when device_ptrs."""
+        self.L = _lib.load()
+        self.conf = make_conf(1, comparator=comparator, partitioner=PART_GIVEN, device=device)
+        self._keep = []
+        arr = (Segment * max(1, len(segments)))()
+        flags = (SEG_HAS_HEADER if has_header else 0) | (SEG_DEVICE if device_ptrs else 0)
+        for i, s in enumerate(segments):
+            if device_ptrs:
+                arr[i].data, arr[i].len = s
+            else:
+                a = np.ascontiguousarray(np.frombuffer(s, dtype=np.uint8) if isinstance(s, (bytes, bytearray)) else s)
+                self._keep.append(a)
+                arr[i].data = a.ctypes.data if a.size else None
+                arr[i].len = a.size
+            arr[i].flags = flags
+        self.h = C.c_void_p()
+        check(self.L.tezgpu_merge_open(C.byref(self.conf), arr, len(segments), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.L.tezgpu_merge_close(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def counts(self):
+        r, b = C.c_uint64(), C.c_uint64()
+        check(self.L.tezgpu_merge_counts(self.h, C.byref(r), C.byref(b)))
+        return r.value, b.value
+
+    def records(self, batch_records=1 << 16, batch_bytes=1 << 24):
+        """Iterates (key, value, is_same_key) like TezRawKeyValueIterator.next/getKey/getValue/isSameKey."""
+        buf = np.empty(batch_bytes, dtype=np.uint8)
+        idx = (KvIndex * batch_records)()
+        n = C.c_uint32()
+        while True:
+            check(self.L.tezgpu_merge_next_batch(self.h, _ptr(buf), buf.size, idx, batch_records, C.byref(n)))
+            if n.value == 0:
+                return
+            raw = buf.tobytes()
+            for i in range(n.value):
+                e = idx[i]
+                yield (raw[e.key_off:e.key_off + e.key_len], raw[e.val_off:e.val_off + e.val_len], bool(e.same_key))
+
+    def output_bound(self):
+        return self.L.tezgpu_merge_output_bound(self.h)
+
+    def write_ifile(self, rle=False, path=None):
+        """TezMerger.writeFile into an IFile.Writer(rle). Returns (segment bytes or None, rawLen, partLen, stats)."""
+        raw, part = C.c_int64(), C.c_int64()
+        st = Stats()
+        if path is not None:
+            check(self.L.tezgpu_merge_write_ifile(self.h, path.encode(), None, 0, 1 if rle else 0, C.byref(raw),
+                                                  C.byref(part), C.byref(st)))
+            return None, raw.value, part.value, st.as_dict()
+        out = np.empty(self.output_bound(), dtype=np.uint8)
+        check(self.L.tezgpu_merge_write_ifile(self.h, None, _ptr(out), out.size, 1 if rle else 0, C.byref(raw),
+                                              C.byref(part), C.byref(st)))
+        return out[:part.value].tobytes(), raw.value, part.value, st.as_dict()
+
+    def write_ifile_device(self, d_out, out_cap, rle=False):
+        raw, part = C.c_int64(), C.c_int64()
+        st = Stats()
+        check(self.L.tezgpu_merge_write_ifile_device(self.h, d_out, out_cap, 1 if rle else 0, C.byref(raw),
+                                                     C.byref(part), C.byref(st)))
+        return raw.value, part.value, st.as_dict()
+
+    def stream(self):
+        return self.L.tezgpu_merge_stream(self.h)
