@@ -65,7 +65,7 @@ class SortPipeline {
     pbits = partition_bits(c.num_partitions);
     TG_CHECK(pbits <= 31, TEZGPU_E_INVALID, "too many partitions");
     h_small.ensure(4096);
-    small.ensure(4096);
+    small.ensure(16384);
     DeviceConstants::get(c.device);
   }
   ~SortPipeline() {
@@ -111,7 +111,7 @@ class SortPipeline {
     seg_crc.ensure((size_t)P * 4);
     h_small.ensure(4096 + (size_t)P * 24);
 
-    TG_CUDA(cudaMemsetAsync(small.p, 0, 4096, stream));
+    TG_CUDA(cudaMemsetAsync(small.p, 0, 16384, stream));
     TG_CUDA(cudaMemsetAsync(seg_crc.p, 0, (size_t)P * 4, stream));
 
     uint64_t dup_count = 0;
