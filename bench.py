@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- sorted-KV GB/s of the Tez shuffle sort/merge hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+N=1 workload = BASELINE config 2: 1e8 records, 16 B key / 64 B value, 64 partitions (HashPartitioner,
+TezBytesComparator) -> file.out bytes bit-identical to the reference format.  A "step" is one complete pass of the
+hot path over that batch (partition + sort + IFile emit with CRC).
+  value   : KV payload GB/s with the records already resident in HBM (device-timed, CUDA events on the library stream)
+  e2e     : the same metric through the C ABI with HOST buffers (H2D of the records and D2H of file.out inside the
+            timed region) -- the call a Tez task makes
+  roofline: the dominant kernel (gather+emit) against the measured HBM copy bandwidth
+N>1 (torchrun, one rank per GPU): BASELINE config 4 shape, weak scaling -- every rank sorts its own records into
+1024 partitions, partitions are exchanged with an all-to-all over NVLink (owner(p) = p mod N), each rank merges the
+N runs of every partition it owns.
+--impl reference: the CPU restatement of PipelinedSorter (oracle/, "port") timed on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+KEY_LEN, VAL_LEN = 16, 64
+REC = KEY_LEN + VAL_LEN
+OUT_REC = REC + 2                      # vint(16) vint(64) key value
+ALGO_BYTES_PER_RECORD = REC + OUT_REC  # read 80 + write 82 = 162 B / record
+METRIC = "sorted KV GB/s (16B key / 64B val)"
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_sample(cores, per_task):
+    """Bounded sample of the same workload for the CPU arm: `cores` independent PipelinedSorter tasks."""
+    import torch
+    from tez_b200 import synth
+    n = cores * per_task
+    kv = synth.gen_c2(0, n, seed=2, device="cpu").numpy()
+    return kv, n
+
+
+def run_cpu(cores, per_task, steps, warmup, partitions):
+    from oracle import tez_oracle as O
+    kv, n = cpu_sample(cores, per_task)
+    conf = O.sorter_conf(partitions)
+    times = []
+    for i in range(warmup + steps):
+        secs, _ = O.bench_pipelined_fixed(conf, kv, KEY_LEN, VAL_LEN, cores)
+        if i >= warmup:
+            times.append(secs)
+    t = sum(times) / len(times)
+    return n * REC / t / 1e9, t, n
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = min(host_cores(), 64)
+    per_task = args.cpu_records_per_task
+    partitions = 64 if args.gpus == 1 else 1024
+    value, secs, n = run_cpu(cores, per_task, args.steps, args.warmup, partitions)
+    sample = "%d records (%d per task x %d tasks, one PipelinedSorter task per core)" % (n, per_task, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(secs * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args.gpus, args.records),
+        "cpu_baseline": {"value": round(value, 4), "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of PipelinedSorter (oracle/tez_oracle.c), not the JVM: no JDK / Hadoop jars exist in this image",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(gpus, records):
+    if gpus == 1:
+        return {"workload": "BASELINE config 2: %d records, 16B key / 64B value, 64 partitions, HashPartitioner, "
+                            "TezBytesComparator, IFile + CRC32 out" % records,
+                "records": records, "partitions": 64, "l2": "inputs (8 GB) larger than L2, no flush needed"}
+    return {"workload": "BASELINE config 4 shape (weak): %d records per GPU, 1024 partitions, all-to-all by "
+                        "partition owner (p mod N) over NVLink, per-GPU k-way merge" % records,
+            "records_per_gpu": records, "partitions": 1024, "parallelism": "partition-sharded x%d" % gpus,
+            "l2": "inputs larger than L2, no flush needed"}
+
+
+def load_traffic():
+    p = os.path.join(ROOT, "profiles", "emit_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+def single_gpu(args):
+    import torch
+    import tez_b200 as T
+    from tez_b200 import synth
+    n, P = args.records, 64
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    d_kv = synth.gen_c2(0, n, seed=2, device=dev)
+    sorter = T.GpuSorter(P, fixed=(KEY_LEN, VAL_LEN), device=0)
+    cap = n * OUT_REC + 10 * P + 4096
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(sorter.stream(), device=dev)
+
+    def step():
+        return sorter.sort_device_fixed(d_kv.data_ptr(), n, d_out.data_ptr(), cap)
+
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(0)
+    clocks.start()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    launches, emit_ms, stage_ms, sort_ms, ties_ms = 0, [], [], [], []
+    for _ in range(args.steps):
+        out_len, index, st = step()
+        launches += st["kernel_launches"]
+        emit_ms.append(st["ms_emit_kernel"])
+        stage_ms.append(st["ms_stage"])
+        sort_ms.append(st["ms_sort"])
+        ties_ms.append(st["ms_ties"])
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms_step = ev0.elapsed_time(ev1) / args.steps
+    value = n * REC / (ms_step * 1e-3) / 1e9
+    assert out_len == n * OUT_REC + 10 * int((index[:, 1] > 0).sum())
+
+    peak, peak_src = hbm_peak()
+    emit = sum(emit_ms) / len(emit_ms)
+    achieved = n * ALGO_BYTES_PER_RECORD / (emit * 1e-3) / 1e9
+    traffic = load_traffic()
+    roofline = {"bound": "hbm", "kernel": "k_emit<true> (gather + IFile framing + CRC32 + coalesced store)",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_RECORD, "ms_per_launch": round(emit, 4)}
+    pipeline = {"algorithmic_bytes_per_step": n * ALGO_BYTES_PER_RECORD,
+                "achieved": round(n * ALGO_BYTES_PER_RECORD / (ms_step * 1e-3) / 1e9, 1),
+                "frac": round(n * ALGO_BYTES_PER_RECORD / (ms_step * 1e-3) / 1e9 / peak, 4),
+                "ms": {"stage": round(sum(stage_ms) / len(stage_ms), 4), "sort": round(sum(sort_ms) / len(sort_ms), 4),
+                       "ties": round(sum(ties_ms) / len(ties_ms), 4), "emit_kernel": round(emit, 4)}}
+
+    # ---- e2e through the C ABI with host buffers (pinned), H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_kv = torch.empty(n * REC, dtype=torch.uint8, pin_memory=True)
+        h_kv.copy_(d_kv)
+        h_out = torch.empty(cap + 4096, dtype=torch.uint8, pin_memory=True)
+        torch.cuda.synchronize()
+        s2 = T.GpuSorter(P, fixed=(KEY_LEN, VAL_LEN), device=0)
+
+        def e2e_step():
+            s2.reset()
+            s2.collect_fixed(h_kv.data_ptr(), n=n)
+            return s2.flush_to_memory(out=h_out.numpy())
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        esteps = max(1, min(args.steps, args.e2e_steps))
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            out, _, _, st2 = e2e_step()
+        torch.cuda.synchronize()
+        t = (time.perf_counter() - t0) / esteps
+        e2e = {"value": round(n * REC / t / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": n * REC,
+               "d2h_bytes_per_step": int(len(out)), "ms_per_step": round(t * 1e3, 2), "steps": esteps,
+               "api": "tezgpu_sorter_collect_fixed + tezgpu_sorter_flush_to_memory (pinned host buffers)"}
+        s2.close()
+        del h_kv, h_out
+
+    # ---- CPU baseline on this box's host cores (bounded sample)
+    cores = min(host_cores(), 64)
+    cval, csecs, cn = run_cpu(cores, args.cpu_records_per_task, 1, 0, P)
+    cpu = {"value": round(cval, 4), "unit": "GB/s", "cores": cores, "kind": "port",
+           "sample": "%d records (%d per task x %d PipelinedSorter tasks), %.2f s" % (cn, args.cpu_records_per_task, cores, csecs)}
+
+    line = {"metric": METRIC, "value": round(value, 3), "unit": "GB/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(1, n),
+            "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "pipeline": pipeline,
+            "cpu_baseline": cpu}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--records", type=int, default=100_000_000)
+    ap.add_argument("--cpu-records-per-task", type=int, default=1_000_000)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl != "reference":
+        args.warmup = 3
+    if args.impl == "reference":
+        return reference_arm(args)
+    if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        return single_gpu(args)
+    from tez_b200 import multigpu_bench
+    return multigpu_bench.run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

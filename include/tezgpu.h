@@ -80,7 +80,7 @@ typedef struct tezgpu_stats {
   int64_t tie_records;                  /* records that needed key-suffix refinement after the prefix radix sort */
   float ms_stage, ms_sort, ms_ties, ms_emit, ms_total; /* device times of the last flush (CUDA events) */
   int32_t kernel_launches;              /* kernels launched by the last flush / merge */
-  int32_t reserved1;
+  float ms_emit_kernel;                 /* device time of the gather+emit kernel alone (CUDA events around its launch) */
 } tezgpu_stats;
 
 typedef struct tezgpu_sorter tezgpu_sorter;
@@ -123,6 +123,9 @@ uint64_t tezgpu_sorter_output_bound(const tezgpu_sorter *h);
 
 /* replaces ExternalSorter.close() (SORT/ExternalSorter.java:281-288) */
 int32_t tezgpu_sorter_destroy(tezgpu_sorter *h);
+/* forgets the collected records but keeps every device / pinned allocation, so a container-reused task
+ * (tez.am.container.reuse) can run its next output through the same handle */
+int32_t tezgpu_sorter_reset(tezgpu_sorter *h);
 
 /* Device-resident variant (records already in HBM; used by the multi-GPU shuffle and by bench.py's kernel-only
  * measurement).  d_kv: n packed fixed-width records on conf.device; d_partition may be 0.  d_out receives file.out

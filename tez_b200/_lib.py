@@ -20,7 +20,7 @@ class Stats(C.Structure):
                 ("output_bytes_physical", C.c_int64), ("spilled_records", C.c_int64), ("file_out_bytes", C.c_int64),
                 ("num_spills", C.c_int32), ("rle_used", C.c_int32), ("adjacent_equal_keys", C.c_int64),
                 ("tie_records", C.c_int64), ("ms_stage", C.c_float), ("ms_sort", C.c_float), ("ms_ties", C.c_float),
-                ("ms_emit", C.c_float), ("ms_total", C.c_float), ("kernel_launches", C.c_int32), ("reserved1", C.c_int32)]
+                ("ms_emit", C.c_float), ("ms_total", C.c_float), ("kernel_launches", C.c_int32), ("ms_emit_kernel", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
@@ -48,6 +48,7 @@ SYMBOLS = [
     ("tezgpu_sorter_flush_to_memory", C.c_int32, [_V, _V, C.c_uint64, _P(C.c_uint64), _V, _V, _P(Stats)]),
     ("tezgpu_sorter_output_bound", C.c_uint64, [_V]),
     ("tezgpu_sorter_destroy", C.c_int32, [_V]),
+    ("tezgpu_sorter_reset", C.c_int32, [_V]),
     ("tezgpu_sorter_sort_device_fixed", C.c_int32, [_V, _V, _V, C.c_uint64, _V, C.c_uint64, _P(C.c_uint64), _V, _P(Stats)]),
     ("tezgpu_sorter_stream", _V, [_V]),
     ("tezgpu_debug_crc_emulate", C.c_uint32, [_V, C.c_uint64, C.c_uint32, C.c_uint32]),

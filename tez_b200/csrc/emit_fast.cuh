@@ -1,0 +1,260 @@
+// emit_fast.cuh -- gather + IFile emit for fixed-width records whose stride is a multiple of 16 bytes
+// (BASELINE config 2/4: 16 B key + 64 B value).  "Source oriented": every lane moves one aligned 128-bit piece of a
+// source record into the shared-memory image of the output bytes (funnel-shifted to its unaligned destination), the
+// CTA folds the image into the segment CRC32 (two-level interleaved table CRC, constant per-lane alignment
+// multipliers) and streams it to HBM with coalesced 128-bit stores.  CTAs are persistent (grid-stride over tiles) so
+// the CRC tables are staged into shared memory once.
+#pragma once
+#include "sorter_kernels.cuh"
+
+namespace tezgpu {
+
+constexpr int FE_THREADS = 256;
+constexpr int FE_MAX_RECS = 256;
+constexpr int FE_IMG_BYTES = 24 * 1024;
+
+struct TileDesc {
+  uint32_t p;      // partition
+  uint32_t r0;     // first sorted position
+  uint32_t nr;     // records
+  uint32_t flags;  // 1 = first tile of the segment, 2 = last tile
+  uint64_t abs0;   // file offset of the tile's first byte
+  uint64_t after;  // body bytes of the segment that follow this tile's bytes
+};
+
+// one entry per emit tile: raw (unconditioned) CRC remainder of the tile's body bytes
+struct TileCrc {
+  uint32_t raw;
+  uint32_t p;
+  uint64_t after;
+};
+
+__global__ void k_build_tiles(EmitParams e, TileDesc *__restrict__ tiles) {
+  uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= e.tile_start[e.P]) return;
+  int lo = 0, hi = e.P;  // last p with tile_start[p] <= tile
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (e.tile_start[mid] <= tile) lo = mid; else hi = mid;
+  }
+  const uint32_t p = (uint32_t)lo;
+  const uint32_t ps = e.part_start[p], pe = e.part_start[p + 1];
+  const uint32_t k = tile - e.tile_start[p];
+  TileDesc d;
+  d.p = p;
+  d.r0 = ps + k * e.recs_per_tile;
+  d.nr = min(e.recs_per_tile, pe - d.r0);
+  const bool first = (k == 0), last = (d.r0 + d.nr == pe);
+  d.flags = (first ? 1u : 0u) | (last ? 2u : 0u);
+  const uint64_t seg0 = e.seg_start[p];
+  d.abs0 = seg0 + (first ? 0 : 4 + (uint64_t)(d.r0 - ps) * e.rec_size);
+  const uint64_t tile_end = seg0 + 4 + (uint64_t)(d.r0 - ps + d.nr) * e.rec_size + (last ? 2 : 0);
+  d.after = (e.seg_start[p + 1] - 4) - tile_end;
+  tiles[tile] = d;
+}
+
+// folds the per-tile remainders into the per-segment remainder: crc(A||B) = crc(A) * x^(8 len B) xor crc(B)
+__global__ void k_crc_combine(const TileCrc *__restrict__ tc, uint32_t ntiles, const CrcTables *__restrict__ t,
+                              uint32_t *__restrict__ seg_crc) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntiles) return;
+  TileCrc c = tc[i];
+  if (c.raw) atomicXor(&seg_crc[c.p], crc_shift_bytes(t, c.raw, c.after));
+}
+
+__device__ __forceinline__ void sts_b8(uint32_t a, uint32_t v) { asm volatile("st.shared.b8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_b16(uint32_t a, uint32_t v) { asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"((unsigned short)v) : "memory"); }
+__device__ __forceinline__ void sts_b32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// stores 16 bytes at an arbitrary shared-memory byte address without touching neighbouring bytes
+__device__ __forceinline__ void sts16_unaligned(uint32_t a, uint4 v) {
+  const uint32_t al = a & 3u;
+  if (al == 0) {
+    if ((a & 15u) == 0) sts_v4(a, v);
+    else { sts_b32(a, v.x); sts_b32(a + 4, v.y); sts_b32(a + 8, v.z); sts_b32(a + 12, v.w); }
+  } else if (al == 2) {
+    sts_b16(a, v.x & 0xFFFFu);
+    sts_b32(a + 2, __funnelshift_r(v.x, v.y, 16));
+    sts_b32(a + 6, __funnelshift_r(v.y, v.z, 16));
+    sts_b32(a + 10, __funnelshift_r(v.z, v.w, 16));
+    sts_b16(a + 14, v.w >> 16);
+  } else if (al == 1) {
+    sts_b8(a, v.x & 0xFFu);
+    sts_b16(a + 1, (v.x >> 8) & 0xFFFFu);
+    sts_b32(a + 3, __funnelshift_r(v.x, v.y, 24));
+    sts_b32(a + 7, __funnelshift_r(v.y, v.z, 24));
+    sts_b32(a + 11, __funnelshift_r(v.z, v.w, 24));
+    sts_b8(a + 15, v.w >> 24);
+  } else {
+    sts_b8(a, v.x & 0xFFu);
+    sts_b32(a + 1, __funnelshift_r(v.x, v.y, 8));
+    sts_b32(a + 5, __funnelshift_r(v.y, v.z, 8));
+    sts_b32(a + 9, __funnelshift_r(v.z, v.w, 8));
+    sts_b16(a + 13, (v.w >> 8) & 0xFFFFu);
+    sts_b8(a + 15, v.w >> 24);
+  }
+}
+
+__device__ __forceinline__ uint4 ldg_stream_v4(const void *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream_v4(void *p, uint4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+struct FastEmitParams {
+  EmitParams e;
+  const TileDesc *tiles;
+  TileCrc *tile_crc;
+  uint32_t ntiles;
+  uint32_t cpr;        // 16-byte pieces per source record (stride / 16)
+  uint32_t cpr_magic;  // floor(2^32 / cpr) + 1
+  uint32_t stride;
+};
+
+template <int UNROLL>
+__global__ void __launch_bounds__(FE_THREADS) k_emit_fast(FastEmitParams fp) {
+  __shared__ __align__(16) uint8_t s_img[FE_IMG_BYTES];
+  __shared__ uint32_t s_idx[FE_MAX_RECS];
+  __shared__ uint32_t s_tab[4 * 256];    // slice-by-4 tables
+  __shared__ uint32_t s_adv[4 * 256];    // * x^(32*FE_THREADS)
+  __shared__ uint32_t s_adv32[4 * 256];  // * x^(32*32)
+  __shared__ uint32_t s_part[FE_THREADS];
+
+  const EmitParams &e = fp.e;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 4 * 256; i += FE_THREADS) {
+    s_tab[i] = (&e.crc->slice[0][0])[i];
+    s_adv[i] = (&e.crc->adv[0][0])[i];
+    s_adv32[i] = (&e.crc->adv32[0][0])[i];
+  }
+  // constant alignment multipliers: x^(32*(31-lane)) for the final in-warp fold
+  const uint32_t lane_pow = e.crc->pow_word[31 - lane];
+  const uint32_t img_base = (uint32_t)__cvta_generic_to_shared(s_img);
+  const uint8_t *__restrict__ kv = e.rec.kv;
+  const uint32_t rec_size = e.rec_size, hdr_len = e.fixed_hdr_len, stride = fp.stride;
+
+  for (uint32_t tile = blockIdx.x; tile < fp.ntiles; tile += gridDim.x) {
+    const TileDesc td = fp.tiles[tile];
+    const uint32_t nr = td.nr;
+    const bool first_tile = td.flags & 1u, last_tile = td.flags & 2u;
+    __syncthreads();  // previous tile fully written out; tables loaded
+    if ((uint32_t)tid < nr) s_idx[tid] = e.order[td.r0 + tid];
+    const uint64_t abs0 = td.abs0;
+    const uint32_t lead = (uint32_t)(abs0 & 15u);
+    const uint32_t rec0 = lead + (first_tile ? 4u : 0u);            // image offset of the first record
+    const uint32_t body_end = rec0 + nr * rec_size + (last_tile ? 2u : 0u);  // image end
+    __syncthreads();
+
+    // ---- gather: lane <-> (record j, 16-byte piece c); all loads of a thread are issued before its stores
+    const uint32_t npieces = nr * fp.cpr;
+    for (uint32_t q0 = tid; q0 < npieces; q0 += FE_THREADS * UNROLL) {
+      uint4 v[UNROLL];
+      uint32_t dst[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        uint32_t q = q0 + u * FE_THREADS;
+        if (q < npieces) {
+          uint32_t j = fp.cpr == 1 ? q : __umulhi(q, fp.cpr_magic);
+          uint32_t c = q - j * fp.cpr;
+          v[u] = ldg_stream_v4(kv + (uint64_t)s_idx[j] * stride + 16u * c);
+          dst[u] = img_base + rec0 + j * rec_size + hdr_len + 16u * c;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        uint32_t q = q0 + u * FE_THREADS;
+        if (q < npieces) sts16_unaligned(dst[u], v[u]);
+      }
+    }
+    // ---- framing: vint(klen) vint(vlen) in front of every record, segment header, EOF markers
+    if ((uint32_t)tid < nr) {
+      uint32_t a = img_base + rec0 + tid * rec_size;
+      for (uint32_t b = 0; b < hdr_len; b++) sts_b8(a + b, e.fixed_hdr[b]);
+    }
+    if (tid == 0) {
+      if (first_tile) { s_img[lead] = 'T'; s_img[lead + 1] = 'I'; s_img[lead + 2] = 'F'; s_img[lead + 3] = 0; }
+      if (last_tile) { s_img[body_end - 2] = 0xFF; s_img[body_end - 1] = 0xFF; }
+    }
+    __syncthreads();
+
+    // ---- CRC of the body bytes [cb0, cb1) of the image.  Leading zero bytes do not change a remainder with zero
+    // initial value, so the (possibly partial) first word is simply masked; trailing bytes are folded in at the end.
+    const uint32_t cb0 = rec0, cb1 = body_end;
+    const uint32_t wa = cb0 >> 2, wb = cb1 >> 2;  // words [wa, wb): first one masked below
+    const uint32_t *img32 = reinterpret_cast<const uint32_t *>(s_img);
+    {
+      // level 1: thread t owns the words whose distance from the end is == T-1-t (mod T): its partial always needs
+      // the same alignment multiplier x^(32*(T-1-t)), whatever the word count
+      uint32_t c = 0;
+      if (wb > wa) {
+        const uint32_t W = wb - wa;
+        const uint32_t head_mask = 0xFFFFFFFFu << (8u * (cb0 & 3u));
+        if (W + tid >= FE_THREADS) {
+          const uint32_t last_i = W - FE_THREADS + tid;
+          uint32_t i = last_i % FE_THREADS;
+          for (; i < last_i; i += FE_THREADS) {
+            uint32_t w = img32[wa + i];
+            if (i == 0) w &= head_mask;
+            uint32_t x = c ^ w;
+            c = s_adv[x & 0xFF] ^ s_adv[256 + ((x >> 8) & 0xFF)] ^ s_adv[512 + ((x >> 16) & 0xFF)] ^ s_adv[768 + (x >> 24)];
+          }
+          uint32_t w = img32[wa + last_i];
+          if (last_i == 0) w &= head_mask;
+          uint32_t x = c ^ w;
+          c = s_tab[768 + (x & 0xFF)] ^ s_tab[512 + ((x >> 8) & 0xFF)] ^ s_tab[256 + ((x >> 16) & 0xFF)] ^ s_tab[x >> 24];
+        }
+      }
+      s_part[tid] = c;
+    }
+    __syncthreads();
+
+    // ---- warps 1..7 stream the image out while warp 0 finishes the checksum
+    if (warp != 0) {
+      uint8_t *dstg = e.out + (abs0 - lead);
+      const uint32_t nchunks = (body_end + 15u) >> 4;
+      for (uint32_t cidx = tid - 32; cidx < nchunks; cidx += FE_THREADS - 32) {
+        uint32_t b0 = 16u * cidx, b1 = b0 + 16u;
+        if (b0 >= lead && b1 <= body_end) {
+          stg_stream_v4(dstg + b0, *reinterpret_cast<const uint4 *>(s_img + b0));
+        } else {
+          uint32_t a = max(b0, lead), b = min(b1, body_end);
+          for (uint32_t x = a; x < b; x++) dstg[x] = s_img[x];
+        }
+      }
+    } else {
+      // level 2: lane l folds partials l, l+32, ... (Horner with x^(32*32)), level 3: align by x^(32*(31-l)), xor-reduce
+      uint32_t q = 0;
+#pragma unroll
+      for (int k = 0; k < FE_THREADS / 32; k++) {
+        q = s_adv32[q & 0xFF] ^ s_adv32[256 + ((q >> 8) & 0xFF)] ^ s_adv32[512 + ((q >> 16) & 0xFF)] ^ s_adv32[768 + (q >> 24)];
+        q ^= s_part[lane + 32 * k];
+      }
+      q = crc_multmodp(q, lane_pow);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q ^= __shfl_xor_sync(0xffffffffu, q, o);
+      if (lane == 0) {
+        uint32_t raw = q;
+        if (wb <= wa) {  // fewer than 4 body bytes: bytewise from cb0
+          raw = 0;
+          for (uint32_t b = cb0; b < cb1; b++) raw = s_tab[(raw ^ s_img[b]) & 0xFF] ^ (raw >> 8);
+        } else {
+          for (uint32_t b = 4 * wb; b < cb1; b++) raw = s_tab[(raw ^ s_img[b]) & 0xFF] ^ (raw >> 8);
+        }
+        TileCrc tc;
+        tc.raw = raw;
+        tc.p = td.p;
+        tc.after = td.after;
+        fp.tile_crc[tile] = tc;
+      }
+    }
+  }
+}
+
+}  // namespace tezgpu

@@ -8,6 +8,16 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef TEZGPU_RADIX_THREADS32
+#define TEZGPU_RADIX_THREADS32 512
+#endif
+#ifndef TEZGPU_RADIX_IPT32
+#define TEZGPU_RADIX_IPT32 16
+#endif
+#ifndef TEZGPU_RANK_MODE
+#define TEZGPU_RANK_MODE 2
+#endif
+
 namespace tezgpu {
 
 constexpr int RADIX_BITS = 8;
@@ -73,11 +83,11 @@ struct OnesweepCfg {
   static constexpr int NWARPS = THREADS / 32;
   static constexpr int TILE = THREADS * IPT;
   static constexpr size_t SMEM = (size_t)TILE * (sizeof(KeyT) + sizeof(uint32_t)) + (size_t)NWARPS * RADIX * 4 +
-                                 2 * RADIX * 4 + 64;
+                                 2 * RADIX * 4 + 64 + (TEZGPU_RANK_MODE == 2 ? (size_t)NWARPS * RADIX * 4 : 0);
 };
 
 template <typename KeyT, int THREADS, int IPT, bool VALS_IOTA>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
     k_onesweep_pass(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, const uint32_t *__restrict__ vals_in,
                     uint32_t *__restrict__ vals_out, uint32_t n, int shift, const uint32_t *__restrict__ hist_base,
                     uint32_t *tile_state, uint32_t *tile_counter) {
@@ -93,11 +103,17 @@ __global__ void __launch_bounds__(THREADS)
   uint32_t *s_dstart = s_wcnt + NWARPS * RADIX;  // [RADIX] tile-local start of each digit
   uint32_t *s_goff = s_dstart + RADIX;        // [RADIX] global offset - local start
   uint32_t *s_misc = s_goff + RADIX;          // [0]=tile id, [1..8] warp scan scratch
+#if TEZGPU_RANK_MODE == 2
+  uint32_t *s_wmask = s_misc + 16;            // [NWARPS][RADIX] warp-private peer bit tables
+#endif
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) s_misc[0] = atomicAdd(tile_counter, 1u);
   for (int i = tid; i < NWARPS * RADIX; i += THREADS) s_wcnt[i] = 0;
+#if TEZGPU_RANK_MODE == 2
+  for (int i = tid; i < NWARPS * RADIX; i += THREADS) s_wmask[i] = 0;
+#endif
   __syncthreads();
   const uint32_t tile = s_misc[0];
   const uint32_t tile_base = tile * (uint32_t)TILE;
@@ -114,17 +130,41 @@ __global__ void __launch_bounds__(THREADS)
   }
   uint32_t *wc = s_wcnt + warp * RADIX;
   const uint32_t lt = lanemask_lt();
+  // warp-private digit counters: the first lane of every group of equal digits claims the group's slots with one
+  // shared-memory atomic (no warp barriers; the atomics of successive items pipeline)
 #pragma unroll
   for (int j = 0; j < IPT; j++) {
     uint32_t li = warp_base + j * 32 + lane;
     bool valid = li < tile_n;
     uint32_t d = radix_digit(key[j], shift);
-    uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : (uint32_t)RADIX);
+    uint32_t peers;
+#if TEZGPU_RANK_MODE == 0
+    peers = __match_any_sync(0xffffffffu, valid ? d : (uint32_t)RADIX);
+#elif TEZGPU_RANK_MODE == 2
+    // peer mask through a warp-private shared-memory bit table: every lane ORs its bit into the entry of its digit,
+    // reads the entry back, then removes its own bit again (atomics, so the next row may already be setting bits)
+    {
+      uint32_t *wm = s_wmask + warp * RADIX;
+      if (valid) atomicOr(&wm[d], 1u << lane);
+      __syncwarp();
+      peers = valid ? wm[d] : 0u;
+      __syncwarp();
+      if (valid) atomicAnd(&wm[d], ~(1u << lane));
+    }
+#else
+    // MATCH.ANY runs on the (slow) ADU pipe; eight ballots + logic ops build the same peer mask on the ALU path
+    peers = __ballot_sync(0xffffffffu, valid);
+    if (!valid) peers = ~peers;
+#pragma unroll
+    for (int b = 0; b < RADIX_BITS; b++) {
+      const bool bit = (d >> b) & 1u;
+      const uint32_t bm = __ballot_sync(0xffffffffu, bit);
+      peers &= bit ? bm : ~bm;
+    }
+#endif
     uint32_t pre = 0;
-    if (valid) pre = wc[d];
-    __syncwarp();
-    if (valid && (peers & lt) == 0) wc[d] = pre + __popc(peers);
-    __syncwarp();
+    if (valid && (peers & lt) == 0) pre = atomicAdd(&wc[d], (uint32_t)__popc(peers));
+    pre = __shfl_sync(0xffffffffu, pre, __ffs(peers) - 1);
     rnk[j] = pre + __popc(peers & lt);
   }
   __syncthreads();
@@ -178,14 +218,24 @@ __global__ void __launch_bounds__(THREADS)
   if (tid < RADIX) {
     uint32_t excl = 0;
     if (tile > 0) {
+      // look back over the predecessors' published counts, LOOKBACK states per round trip (independent loads)
+      constexpr int LOOKBACK = 8;
       int64_t t = (int64_t)tile - 1;
-      while (true) {
-        uint32_t s = ld_volatile_u32(&tile_state[(size_t)t * RADIX + tid]);
-        uint32_t flag = s & ~STATE_VALUE_MASK;
-        if (flag == 0) continue;  // predecessor has not published yet
-        excl += s & STATE_VALUE_MASK;
-        if (flag == STATE_FLAG_INCL) break;
-        t--;
+      bool done = false;
+      while (!done) {
+        uint32_t st[LOOKBACK];
+#pragma unroll
+        for (int b = 0; b < LOOKBACK; b++)
+          st[b] = (t - b >= 0) ? ld_volatile_u32(&tile_state[(size_t)(t - b) * RADIX + tid]) : STATE_FLAG_INCL;
+#pragma unroll
+        for (int b = 0; b < LOOKBACK; b++) {
+          if (done) break;
+          uint32_t flag = st[b] & ~STATE_VALUE_MASK;
+          if (flag == 0) break;  // not published yet: retry from here
+          excl += st[b] & STATE_VALUE_MASK;
+          t--;
+          if (flag == STATE_FLAG_INCL) done = true;
+        }
       }
       st_volatile_u32(&tile_state[(size_t)tile * RADIX + tid], STATE_FLAG_INCL | (excl + count));
     }
@@ -217,8 +267,8 @@ struct RadixWorkspace {
 
 template <typename KeyT>
 struct RadixTuning {
-  static constexpr int THREADS = 512;
-  static constexpr int IPT = sizeof(KeyT) == 4 ? 16 : 10;
+  static constexpr int THREADS = sizeof(KeyT) == 4 ? TEZGPU_RADIX_THREADS32 : 512;
+  static constexpr int IPT = sizeof(KeyT) == 4 ? TEZGPU_RADIX_IPT32 : 10;
 };
 
 template <typename KeyT>

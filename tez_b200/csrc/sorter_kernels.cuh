@@ -109,20 +109,43 @@ __device__ __forceinline__ void tie_flags(const uint32_t *__restrict__ K, uint32
   head = tied && !eq_prev;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_tie_count(const uint32_t *__restrict__ K, uint32_t n,
-                                                            uint64_t *__restrict__ blk) {
-  __shared__ uint64_t s_warp[SCAN_THREADS / 32];
-  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
-  uint64_t s = 0;
+// Ordered block-level ranking of two flag sets over a tile processed in striped rows (row k holds elements
+// k*THREADS + tid): returns, for this thread's element of row k, the number of flagged elements that precede it in
+// index order, for both flag sets packed as (tied | heads << 32).  s_cnt: [SCAN_IPT][SCAN_THREADS/32] u64.
+struct TileFlags {
+  bool t[SCAN_IPT], h[SCAN_IPT];
+};
+
+__device__ __forceinline__ void tile_load_flags(const uint32_t *__restrict__ K, uint32_t n, uint32_t *s_k, TileFlags &f) {
+  const uint32_t base = blockIdx.x * SCAN_TILE;
+  for (uint32_t i = threadIdx.x; i < SCAN_TILE + 2; i += SCAN_THREADS) {
+    int64_t gi = (int64_t)base + i - 1;
+    s_k[i] = (gi >= 0 && gi < (int64_t)n) ? K[gi] : 0u;
+  }
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < SCAN_IPT; k++) {
-    uint32_t i = base + k;
+    uint32_t li = k * SCAN_THREADS + threadIdx.x, i = base + li;
+    f.t[k] = f.h[k] = false;
     if (i < n) {
-      bool t, h;
-      tie_flags(K, n, i, t, h);
-      s += (uint64_t)t | ((uint64_t)h << 32);
+      uint32_t v = s_k[li + 1];
+      bool eq_prev = i > 0 && s_k[li] == v;
+      bool eq_next = i + 1 < n && s_k[li + 2] == v;
+      f.t[k] = eq_prev || eq_next;
+      f.h[k] = f.t[k] && !eq_prev;
     }
   }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_tie_count(const uint32_t *__restrict__ K, uint32_t n,
+                                                            uint64_t *__restrict__ blk) {
+  __shared__ uint32_t s_k[SCAN_TILE + 2];
+  __shared__ uint64_t s_warp[SCAN_THREADS / 32];
+  TileFlags f;
+  tile_load_flags(K, n, s_k, f);
+  uint64_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; k++) s += (uint64_t)f.t[k] | ((uint64_t)f.h[k] << 32);
   uint64_t tot;
   block_exclusive_scan_u64(s, s_warp, &tot);
   if (threadIdx.x == 0) blk[blockIdx.x] = tot;
@@ -133,29 +156,100 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     k_tie_compact(const uint32_t *__restrict__ K, const uint32_t *__restrict__ order, uint32_t n,
                   const uint64_t *__restrict__ blk, uint32_t *__restrict__ pos, uint32_t *__restrict__ gid,
                   uint32_t *__restrict__ lidx) {
-  __shared__ uint64_t s_warp[SCAN_THREADS / 32];
-  uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
-  bool t[SCAN_IPT], h[SCAN_IPT];
-  uint64_t s = 0;
+  __shared__ uint32_t s_k[SCAN_TILE + 2];
+  __shared__ uint32_t s_ct[SCAN_IPT][SCAN_THREADS / 32], s_ch[SCAN_IPT][SCAN_THREADS / 32];
+  TileFlags f;
+  tile_load_flags(K, n, s_k, f);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = lanemask_lt();
+  uint32_t bt[SCAN_IPT], bh[SCAN_IPT];
 #pragma unroll
   for (int k = 0; k < SCAN_IPT; k++) {
-    uint32_t i = base + k;
-    t[k] = h[k] = false;
-    if (i < n) tie_flags(K, n, i, t[k], h[k]);
-    s += (uint64_t)t[k] | ((uint64_t)h[k] << 32);
+    bt[k] = __ballot_sync(0xffffffffu, f.t[k]);
+    bh[k] = __ballot_sync(0xffffffffu, f.h[k]);
+    if (lane == 0) { s_ct[k][warp] = __popc(bt[k]); s_ch[k][warp] = __popc(bh[k]); }
   }
-  uint64_t ex = block_exclusive_scan_u64(s, s_warp, nullptr) + blk[blockIdx.x];
-  uint32_t at = (uint32_t)ex, heads = (uint32_t)(ex >> 32);
+  __syncthreads();
+  // exclusive prefix over (row, warp) in index order; rows are few, so every thread walks the small table
+  const uint64_t b0 = blk[blockIdx.x];
+  uint32_t run_t = (uint32_t)b0, run_h = (uint32_t)(b0 >> 32);
+  const uint32_t base = blockIdx.x * SCAN_TILE;
 #pragma unroll
   for (int k = 0; k < SCAN_IPT; k++) {
-    if (t[k]) {
-      if (h[k]) heads++;
-      uint32_t i = base + k;
+    uint32_t pre_t = run_t, pre_h = run_h;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) {
+      uint32_t ct = s_ct[k][w], ch = s_ch[k][w];
+      if (w < warp) { pre_t += ct; pre_h += ch; }
+      run_t += ct; run_h += ch;
+    }
+    if (f.t[k]) {
+      uint32_t at = pre_t + __popc(bt[k] & lt);
+      uint32_t heads = pre_h + __popc(bh[k] & lt) + (f.h[k] ? 1u : 0u);  // heads up to and including this element
+      uint32_t i = base + k * SCAN_THREADS + threadIdx.x;
       pos[at] = i;
       gid[at] = heads - 1;
       lidx[at] = order[i];
-      at++;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ small tie groups
+// full RawComparator order of two records' keys from normalised content byte `depth` on (bytes before it are equal)
+__device__ __forceinline__ int compare_keys_from(const Records &r, uint32_t ra, uint32_t rb, uint32_t depth) {
+  uint64_t ka, kb;
+  uint32_t la, lb, va, vb;
+  record_lookup(r, ra, ka, la, va);
+  record_lookup(r, rb, kb, lb, vb);
+  const uint8_t *a = r.kv + ka, *b = r.kv + kb;
+  uint32_t sa = key_content_skip(r.cmp, a, la), sb = key_content_skip(r.cmp, b, lb);
+  a += sa; b += sb; la -= sa; lb -= sb;
+  uint32_t nmin = la < lb ? la : lb;
+  for (uint32_t i = depth; i < nmin; i++) {
+    uint32_t x = norm_byte(r.cmp, a, i), y = norm_byte(r.cmp, b, i);
+    if (x != y) return x < y ? -1 : 1;
+  }
+  return la < lb ? -1 : (la == lb ? 0 : 1);
+}
+
+constexpr uint32_t TIE_SMALL_MAX = 16;
+
+// One thread per tied record: groups of at most TIE_SMALL_MAX records are ordered directly with the full comparator
+// (rank = #smaller + #equal-and-earlier).  With uniformly distributed keys almost every group has 2-3 members.
+// Larger groups are only counted; the host then runs the radix refinement rounds.
+__global__ void __launch_bounds__(256)
+    k_tie_small(Records r, const uint32_t *__restrict__ pos, const uint32_t *__restrict__ gid,
+                const uint32_t *__restrict__ lidx, uint32_t m, uint32_t depth, uint32_t *__restrict__ order,
+                uint8_t *__restrict__ same, unsigned long long *__restrict__ dup_count,
+                uint32_t *__restrict__ large_groups) {
+  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const uint32_t g = gid[j];
+  uint32_t s = j;
+  while (s > 0 && gid[s - 1] == g && j - s < TIE_SMALL_MAX) s--;
+  bool large = (s > 0 && gid[s - 1] == g);
+  uint32_t e = j + 1;
+  if (!large) {
+    while (e < m && gid[e] == g && e - s <= TIE_SMALL_MAX) e++;
+    large = (e - s > TIE_SMALL_MAX);
+  }
+  if (large) {
+    if (j == 0 || gid[j - 1] != g) atomicAdd(large_groups, 1u);
+    return;
+  }
+  const uint32_t me = lidx[j];
+  uint32_t rank = 0, eq_before = 0;
+  for (uint32_t q = s; q < e; q++) {
+    if (q == j) continue;
+    int c = compare_keys_from(r, lidx[q], me, depth);
+    if (c < 0) rank++;
+    else if (c == 0 && q < j) { rank++; eq_before++; }
+  }
+  const uint32_t p = pos[s + rank];
+  order[p] = me;
+  if (eq_before) {
+    same[p] = 1;  // byte-identical to the key at sorted position p-1
+    atomicAdd(dup_count, 1ull);
   }
 }
 

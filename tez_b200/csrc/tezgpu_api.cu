@@ -138,6 +138,15 @@ int32_t tezgpu_sorter_destroy(tezgpu_sorter *h) {
   TG_API_END
 }
 
+int32_t tezgpu_sorter_reset(tezgpu_sorter *h) {
+  TG_API_BEGIN
+  TG_CHECK(h, TEZGPU_E_INVALID, "null handle");
+  h->n = h->kv_bytes = h->payload_bytes = 0;
+  h->has_partition = false;
+  h->flushed = false;
+  TG_API_END
+}
+
 int32_t tezgpu_sorter_collect_batch(tezgpu_sorter *h, const uint8_t *kv, uint64_t kv_bytes, const uint32_t *key_off,
                                     const uint32_t *val_off, const uint32_t *val_len, const int32_t *partition,
                                     uint32_t n) {
@@ -215,6 +224,9 @@ int32_t tezgpu_sorter_collect_fixed(tezgpu_sorter *h, const uint8_t *kv, const i
 
 uint64_t tezgpu_sorter_output_bound(const tezgpu_sorter *h) {
   if (!h) return 0;
+  if (h->fixed && h->pipe.conf.rle_policy == TEZGPU_RLE_OFF)  // exact: n * (vint(k) + vint(v) + k + v) + 10 bytes per segment
+    return h->n * ((uint64_t)vint_size_u32(h->klen) + vint_size_u32(h->vlen) + h->klen + h->vlen) +
+           10ull * h->pipe.conf.num_partitions + 64;
   return SortPipeline::output_bound(h->n, h->kv_bytes, h->pipe.conf.num_partitions);
 }
 

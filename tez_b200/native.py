@@ -76,23 +76,24 @@ class GpuSorter:
             partition = np.ascontiguousarray(partition, dtype=np.int32)
         check(self.L.tezgpu_sorter_collect_fixed(self.h, p, _ptr(partition), n))
 
+    def reset(self):
+        check(self.L.tezgpu_sorter_reset(self.h))
+
     def output_bound(self):
         return self.L.tezgpu_sorter_output_bound(self.h)
 
     def flush_to_memory(self, out=None):
         """Returns (file_out uint8 array view, index_bytes, index[P,3], stats dict)."""
-        cap = self.output_bound()
         if out is None:
-            out = np.empty(cap, dtype=np.uint8)
+            out = np.empty(self.output_bound(), dtype=np.uint8)
+        cap = out.size
         n = C.c_uint64()
         index = np.zeros((self.P, 3), dtype=np.int64)
         index_bytes = np.zeros(self.P * 24 + 8, dtype=np.uint8)
         st = Stats()
-        check(self.L.tezgpu_sorter_flush_to_memory(self.h, _ptr(out) if not isinstance(out, int) else out,
-                                                   cap if not isinstance(out, int) else cap, C.byref(n),
-                                                   _ptr(index_bytes), _ptr(index), C.byref(st)))
-        res = out[:n.value] if not isinstance(out, int) else n.value
-        return res, index_bytes.tobytes(), index, st.as_dict()
+        check(self.L.tezgpu_sorter_flush_to_memory(self.h, _ptr(out), cap, C.byref(n), _ptr(index_bytes), _ptr(index),
+                                                   C.byref(st)))
+        return out[:n.value], index_bytes.tobytes(), index, st.as_dict()
 
     def flush(self, out_path, index_path):
         index = np.zeros((self.P, 3), dtype=np.int64)
