@@ -1,3 +1,527 @@
-// merger.cuh -- reduce-side k-way merge on device (placeholder until the merge kernels land).
+// merger.cuh -- reduce side of the hot path on sm_100a: k-way merge of sorted IFile segments.
+// Device counterpart of TezMerger.MergeQueue (SORT/TezMerger.java:465-1065): segments are checksum-verified and
+// parsed on the device, the union of their records is ordered with the same radix-sort + key-refinement machinery
+// as the map side (a stable sort of already sorted runs IS their k-way merge: equal keys keep (segment, position)
+// order), and the merged stream is either iterated (TezRawKeyValueIterator) or written as one IFile segment
+// (TezMerger.writeFile, :215-245) with REPEAT_KEY run-length encoding of equal adjacent keys.
 #pragma once
+#include <vector>
+
 #include "sorter.cuh"
+
+namespace tezgpu {
+
+struct SegDesc {
+  uint64_t off;       // offset of the segment in the staging buffer (16-byte aligned)
+  uint64_t len;       // total bytes
+  uint64_t body0;     // offset of the first body byte inside the segment (4 with header, 0 in-memory)
+  uint64_t body_end;  // offset just past the EOF markers' possible position: len - 4 (checksum / slack excluded)
+  uint32_t has_header;
+  uint32_t pad;
+};
+
+// ------------------------------------------------------------------------------------------------ checksum
+// raw CRC remainder of 64 KiB pieces of the segment bodies, combined per segment by k_crc_combine
+constexpr uint32_t CRC_PIECE = 64 * 1024;
+constexpr int CRCV_THREADS = 256;
+
+__global__ void __launch_bounds__(CRCV_THREADS)
+    k_crc_pieces(const uint8_t *__restrict__ data, const SegDesc *__restrict__ segs, const uint32_t *__restrict__ piece_start,
+                 uint32_t nseg, const CrcTables *__restrict__ t, TileCrc *__restrict__ out) {
+  __shared__ uint32_t s_tab[4 * 256], s_adv[4 * 256], s_adv32[4 * 256], s_part[CRCV_THREADS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < 4 * 256; i += CRCV_THREADS) {
+    s_tab[i] = (&t->slice[0][0])[i];
+    s_adv[i] = (&t->adv[0][0])[i];
+    s_adv32[i] = (&t->adv32[0][0])[i];
+  }
+  const uint32_t piece = blockIdx.x;
+  uint32_t lo = 0, hi = nseg;  // last segment with piece_start[s] <= piece
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (piece_start[mid] <= piece) lo = mid; else hi = mid;
+  }
+  const SegDesc sd = segs[lo];
+  const uint64_t body_bytes = sd.body_end - sd.body0;
+  const uint64_t a = (uint64_t)(piece - piece_start[lo]) * CRC_PIECE;
+  const uint64_t b = min(body_bytes, a + CRC_PIECE);
+  const uint8_t *base = data + sd.off + sd.body0;  // 4-byte aligned (segments start 16-byte aligned, body0 in {0,4})
+  const uint32_t W = (uint32_t)((b - a) >> 2);
+  const uint32_t *w32 = reinterpret_cast<const uint32_t *>(base + a);
+  __syncthreads();
+  uint32_t c = 0;
+  if (W + tid >= CRCV_THREADS && W > 0) {
+    const uint32_t last_i = W - CRCV_THREADS + tid;
+    uint32_t i = last_i % CRCV_THREADS;
+    for (; i < last_i; i += CRCV_THREADS) {
+      uint32_t x = c ^ w32[i];
+      c = s_adv[x & 0xFF] ^ s_adv[256 + ((x >> 8) & 0xFF)] ^ s_adv[512 + ((x >> 16) & 0xFF)] ^ s_adv[768 + (x >> 24)];
+    }
+    uint32_t x = c ^ w32[last_i];
+    c = s_tab[768 + (x & 0xFF)] ^ s_tab[512 + ((x >> 8) & 0xFF)] ^ s_tab[256 + ((x >> 16) & 0xFF)] ^ s_tab[x >> 24];
+  }
+  s_part[tid] = c;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t q = 0;
+#pragma unroll
+    for (int k = 0; k < CRCV_THREADS / 32; k++) {
+      q = s_adv32[q & 0xFF] ^ s_adv32[256 + ((q >> 8) & 0xFF)] ^ s_adv32[512 + ((q >> 16) & 0xFF)] ^ s_adv32[768 + (q >> 24)];
+      q ^= s_part[lane + 32 * k];
+    }
+    q = crc_multmodp(q, t->pow_word[31 - lane]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q ^= __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) {
+      uint32_t raw = q;
+      for (uint64_t x = a + 4ull * W; x < b; x++) raw = s_tab[(raw ^ base[x]) & 0xFF] ^ (raw >> 8);
+      TileCrc tc;
+      tc.raw = raw;
+      tc.p = lo;
+      tc.after = body_bytes - b;
+      out[piece] = tc;
+    }
+  }
+}
+
+// compares the folded remainder with the big-endian trailer (SORT/IFileInputStream.java:235-289)
+__global__ void k_crc_check(const uint8_t *__restrict__ data, const SegDesc *__restrict__ segs, uint32_t nseg,
+                            const uint32_t *__restrict__ seg_crc, const CrcTables *__restrict__ t, int *__restrict__ bad) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  const SegDesc sd = segs[s];
+  if (!sd.has_header) return;  // in-memory segments carry no checksum stream (OG/InMemoryReader.java:142-254)
+  const uint64_t body = sd.body_end - sd.body0;
+  uint32_t crc = seg_crc[s] ^ crc_shift_bytes(t, 0xFFFFFFFFu, body) ^ 0xFFFFFFFFu;
+  const uint8_t *tr = data + sd.off + sd.body_end;
+  uint32_t stored = ((uint32_t)tr[0] << 24) | ((uint32_t)tr[1] << 16) | ((uint32_t)tr[2] << 8) | tr[3];
+  if (crc != stored) atomicExch(bad, (int)s + 1);
+}
+
+// ------------------------------------------------------------------------------------------------ parse
+// hadoop WritableUtils.readVLong with bounds; returns false when the buffer ends inside the vint
+__device__ __forceinline__ bool read_vlong_dev(const uint8_t *p, uint64_t &pos, uint64_t end, int64_t &out) {
+  if (pos >= end) return false;
+  int8_t first = (int8_t)p[pos];
+  int len = vint_decode_size((uint8_t)first);
+  if (pos + (uint64_t)len > end) return false;
+  if (len == 1) { out = first; pos += 1; return true; }
+  uint64_t v = 0;
+  for (int i = 1; i < len; i++) v = (v << 8) | p[pos + i];
+  bool neg = first < -120 || (first >= -112 && first < 0);
+  out = neg ? (int64_t)~v : (int64_t)v;
+  pos += len;
+  return true;
+}
+
+struct ParseArrays {
+  uint64_t *key_off;
+  uint64_t *val_off;
+  uint32_t *key_len;
+  uint32_t *val_len;
+  uint32_t *tag;  // (segment << 1) | read as SAME_KEY (run-length encoded in the input)
+};
+
+// Walks one segment with IFile.Reader semantics (positionToNextRecord / readRawKey / nextRawValue,
+// SORT/IFile.java:877-1000).  EMIT=false counts records, EMIT=true writes their metadata at rec_base[s]...
+template <bool EMIT>
+__global__ void k_parse_segments(const uint8_t *__restrict__ data, const SegDesc *__restrict__ segs, uint32_t nseg,
+                                 uint64_t *__restrict__ counts /*[nseg] records*/, uint64_t *__restrict__ kvbytes /*[nseg]*/,
+                                 const uint64_t *__restrict__ rec_base, ParseArrays out, int *__restrict__ bad) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  const SegDesc sd = segs[s];
+  const uint8_t *p = data + sd.off;
+  uint64_t pos = sd.body0;
+  const uint64_t end = sd.body_end;
+  int64_t cur_klen = 0, cur_vlen = 0;
+  uint64_t orig_koff = 0;
+  int64_t orig_klen = 0;
+  uint64_t n = 0, bytes = 0;
+  const uint64_t base = EMIT ? rec_base[s] : 0;
+  bool ok = true;
+  while (true) {
+    if (cur_klen == -2) {  // previous record was a repeat: only a value length follows (readValueLength :877-883)
+      if (!read_vlong_dev(p, pos, end, cur_vlen)) { ok = false; break; }
+      if (cur_vlen == -3) {
+        if (!read_vlong_dev(p, pos, end, cur_klen) || !read_vlong_dev(p, pos, end, cur_vlen)) { ok = false; break; }
+      }
+    } else {
+      if (!read_vlong_dev(p, pos, end, cur_klen) || !read_vlong_dev(p, pos, end, cur_vlen)) { ok = false; break; }
+    }
+    if (cur_klen == -1 && cur_vlen == -1) break;  // EOF markers
+    if ((cur_klen != -2 && cur_klen < 0) || cur_vlen < 0 || cur_klen > 0x7fffffffll || cur_vlen > 0x7fffffffll) { ok = false; break; }
+    if (cur_klen != -2) {
+      if (pos + (uint64_t)cur_klen > end) { ok = false; break; }
+      orig_koff = pos;
+      orig_klen = cur_klen;
+      pos += (uint64_t)cur_klen;
+    } else if (n == 0) { ok = false; break; }  // a repeat needs a previous key
+    if (pos + (uint64_t)cur_vlen > end) { ok = false; break; }
+    if (EMIT) {
+      // a repeated key points at the bytes of the last full key; its value bytes are not adjacent to it
+      out.key_off[base + n] = sd.off + orig_koff;
+      out.val_off[base + n] = sd.off + pos;
+      out.key_len[base + n] = (uint32_t)orig_klen;
+      out.val_len[base + n] = (uint32_t)cur_vlen;
+      out.tag[base + n] = (s << 1) | (cur_klen == -2 ? 1u : 0u);
+    }
+    n++;
+    bytes += (uint64_t)orig_klen + (uint64_t)cur_vlen;
+    pos += (uint64_t)cur_vlen;
+  }
+  if (!ok) atomicExch(bad, (int)s + 1);
+  if (!EMIT) { counts[s] = n; kvbytes[s] = bytes; }
+}
+
+
+// fixed-width shortcut (multi-GPU shuffle of device-sorted partitions): when the body is exactly n records of a
+// known framing and every record position carries that framing, the sequential walk would visit exactly these
+// positions, so the metadata is pure arithmetic.  ok[s] = 0 if any position disagrees.
+__global__ void k_parse_fixed_check(const uint8_t *__restrict__ data, const SegDesc *__restrict__ segs, uint32_t nseg,
+                                    const uint64_t *__restrict__ rec_base, uint32_t klen, uint32_t vlen, uint32_t hdr_len,
+                                    uint64_t hdr_bytes /*packed little-endian*/, ParseArrays out, int *__restrict__ mismatch) {
+  const uint64_t total = rec_base[nseg];
+  const uint32_t rs = hdr_len + klen + vlen;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t lo = 0, hi = nseg;  // segment of record i
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (rec_base[mid] <= i) lo = mid; else hi = mid;
+    }
+    const SegDesc sd = segs[lo];
+    const uint64_t pos = sd.off + sd.body0 + (i - rec_base[lo]) * rs;
+    bool ok = true;
+    for (uint32_t b = 0; b < hdr_len; b++) ok &= data[pos + b] == (uint8_t)(hdr_bytes >> (8 * b));
+    if (!ok) *mismatch = 1;
+    out.key_off[i] = pos + hdr_len;
+    out.val_off[i] = pos + hdr_len + klen;
+    out.key_len[i] = klen;
+    out.val_len[i] = vlen;
+    out.tag[i] = lo << 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ iterator batches
+// kv_off[r] = sum of (klen + vlen) of the merged records before sorted position r
+__global__ void __launch_bounds__(256) k_kv_sizes(Records rec, const uint32_t *__restrict__ order, uint32_t *__restrict__ sizes) {
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rec.n) return;
+  uint32_t i = order[r];
+  sizes[r] = rec.key_len[i] + rec.val_len[i];
+}
+
+// largest count <= max_records starting at `cursor` whose key+value bytes fit in cap
+__global__ void k_find_batch(const uint64_t *__restrict__ kv_off, uint32_t n, uint32_t cursor, uint32_t max_records,
+                             uint64_t cap, uint32_t *__restrict__ out_count) {
+  uint32_t lo = 0, hi = min(max_records, n - cursor);
+  const uint64_t base = kv_off[cursor];
+  while (lo < hi) {
+    uint32_t mid = lo + (hi - lo + 1) / 2;
+    if (kv_off[cursor + mid] - base <= cap) lo = mid; else hi = mid - 1;
+  }
+  *out_count = lo;
+}
+
+struct KvIndexDev { uint32_t key_off, key_len, val_off, val_len, same_key; };
+
+// one warp per record: copies key then value bytes into the batch buffer and fills the index entry
+__global__ void __launch_bounds__(256)
+    k_gather_batch(Records rec, const uint32_t *__restrict__ order, const uint8_t *__restrict__ same,
+                   const uint64_t *__restrict__ kv_off, uint32_t cursor, uint32_t count, uint8_t *__restrict__ out,
+                   KvIndexDev *__restrict__ idx) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= count) return;
+  const uint32_t r = cursor + w, i = order[r];
+  const uint64_t o = kv_off[r] - kv_off[cursor];
+  const uint32_t kl = rec.key_len[i], vl = rec.val_len[i];
+  const uint8_t *k = rec.kv + rec.key_off[i];
+  const uint8_t *v = rec.kv + (rec.val_off ? rec.val_off[i] : rec.key_off[i] + kl);
+  for (uint32_t b = lane; b < kl; b += 32) out[o + b] = k[b];
+  for (uint32_t b = lane; b < vl; b += 32) out[o + kl + b] = v[b];
+  if (lane == 0) {
+    KvIndexDev e;
+    e.key_off = (uint32_t)o; e.key_len = kl; e.val_off = (uint32_t)(o + kl); e.val_len = vl;
+    // MergeQueue.isSameKey(): read as SAME_KEY from its segment, or equal to the previous key of another segment
+    bool sk = false;
+    if (r > 0 && same[r]) {
+      const uint32_t tag = rec.tag[i], tagp = rec.tag[order[r - 1]];
+      sk = (tag & 1u) || ((tag >> 1) != (tagp >> 1));
+    }
+    e.same_key = sk ? 1u : 0u;
+    idx[w] = e;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host orchestration
+class Merger {
+ public:
+  SortPipeline pipe;
+  DeviceBuffer d_data, d_segs, d_piece_start, d_piece_crc, d_seg_crc, d_counts, d_rec_base;
+  DeviceBuffer d_koff, d_voff, d_klen, d_vlen, d_tag, d_sizes, d_kvoff, d_batch, d_batch_idx, d_out;
+  PinnedBuffer h_stage, h_out;
+  std::vector<SegDesc> segs;
+  uint64_t n = 0, kv_bytes = 0, seg_bytes = 0, cursor = 0;
+  bool have_kvoff = false;
+  int launches = 0;
+  const uint8_t *data = nullptr;  // base of the segment bytes on the device
+
+  static tezgpu_conf pipe_conf(tezgpu_conf c) {
+    c.num_partitions = 1;
+    c.partitioner = TEZGPU_PART_GIVEN;
+    c.send_empty_partition_details = 0;  // a merge always writes its (possibly empty) segment
+    c.fixed_key_len = c.fixed_val_len = 0;
+    return c;
+  }
+  uint32_t fixed_klen = 0, fixed_vlen = 0;
+
+  explicit Merger(const tezgpu_conf &c) : pipe(pipe_conf(c)), fixed_klen(c.fixed_key_len), fixed_vlen(c.fixed_val_len) {}
+
+  void open(const tezgpu_segment *in, uint32_t nseg) {
+    cudaStream_t st = pipe.stream;
+    TG_CUDA(cudaSetDevice(pipe.conf.device));
+    // ---- stage all segments contiguously (16-byte aligned starts, 32 bytes of slack)
+    segs.resize(nseg);
+    uint64_t off = 0;
+    for (uint32_t s = 0; s < nseg; s++) {
+      TG_CHECK(in[s].data || in[s].len == 0, TEZGPU_E_INVALID, "null segment");
+      const bool hdr = in[s].flags & TEZGPU_SEG_HAS_HEADER;
+      TG_CHECK(in[s].len >= (hdr ? 10u : 6u), TEZGPU_E_FORMAT, "IFile segment shorter than an empty segment");
+      segs[s].off = off;
+      segs[s].len = in[s].len;
+      segs[s].body0 = hdr ? 4 : 0;
+      segs[s].body_end = in[s].len - 4;
+      segs[s].has_header = hdr ? 1 : 0;
+      segs[s].pad = 0;
+      off = align_up(off + in[s].len, 16);
+    }
+    seg_bytes = off;
+    d_data.ensure(off + 64);
+    for (uint32_t s = 0; s < nseg; s++) {
+      if (!in[s].len) continue;
+      const bool dev = in[s].flags & TEZGPU_SEG_DEVICE;
+      TG_CUDA(cudaMemcpyAsync(d_data.as<uint8_t>() + segs[s].off, in[s].data, in[s].len,
+                              dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    }
+    data = d_data.as<uint8_t>();
+    d_segs.ensure((size_t)(nseg ? nseg : 1) * sizeof(SegDesc));
+    if (nseg) TG_CUDA(cudaMemcpyAsync(d_segs.p, segs.data(), (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
+    TG_CUDA(cudaStreamSynchronize(st));  // caller's buffers may go away after open()
+
+    // ---- header checks (verifyHeaderMagic / compressed flag, SORT/IFile.java:1004-1016) on the host copy of 4 bytes
+    for (uint32_t s = 0; s < nseg; s++) {
+      if (!segs[s].has_header) continue;
+      uint8_t h[4];
+      if (in[s].flags & TEZGPU_SEG_DEVICE) TG_CUDA(cudaMemcpy(h, in[s].data, 4, cudaMemcpyDeviceToHost));
+      else memcpy(h, in[s].data, 4);
+      TG_CHECK(h[0] == 'T' && h[1] == 'I' && h[2] == 'F', TEZGPU_E_FORMAT, "Not a valid ifile header");
+      TG_CHECK(h[3] == 0, TEZGPU_E_UNSUPPORTED, "compressed IFile segments are not supported on the device path");
+    }
+
+    const CrcTables *d_crc = DeviceConstants::get(pipe.conf.device).d_crc;
+    int *d_bad = pipe.d_error();
+    TG_CUDA(cudaMemsetAsync(pipe.small.p, 0, 16384, st));
+    if (nseg) {
+      // ---- checksums
+      std::vector<uint32_t> piece_start(nseg + 1);
+      uint32_t np = 0;
+      for (uint32_t s = 0; s < nseg; s++) {
+        piece_start[s] = np;
+        np += (uint32_t)div_up(segs[s].body_end - segs[s].body0, CRC_PIECE);
+      }
+      piece_start[nseg] = np;
+      d_piece_start.ensure((size_t)(nseg + 1) * 4);
+      TG_CUDA(cudaMemcpyAsync(d_piece_start.p, piece_start.data(), (size_t)(nseg + 1) * 4, cudaMemcpyHostToDevice, st));
+      d_piece_crc.ensure((size_t)(np ? np : 1) * sizeof(TileCrc));
+      d_seg_crc.ensure((size_t)nseg * 4);
+      TG_CUDA(cudaMemsetAsync(d_seg_crc.p, 0, (size_t)nseg * 4, st));
+      if (np) {
+        k_crc_pieces<<<np, CRCV_THREADS, 0, st>>>(data, d_segs.as<SegDesc>(), d_piece_start.as<uint32_t>(), nseg, d_crc,
+                                                  d_piece_crc.as<TileCrc>());
+        k_crc_combine<<<(uint32_t)div_up(np, 256), 256, 0, st>>>(d_piece_crc.as<TileCrc>(), np, d_crc, d_seg_crc.as<uint32_t>());
+        launches += 2;
+      }
+      k_crc_check<<<(uint32_t)div_up(nseg, 128), 128, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, d_seg_crc.as<uint32_t>(), d_crc, d_bad);
+      launches++;
+      TG_CUDA(cudaGetLastError());
+      int bad = 0;
+      TG_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+      TG_CUDA(cudaStreamSynchronize(st));
+      TG_CHECK(bad == 0, TEZGPU_E_FORMAT, "IFile checksum mismatch in segment " + std::to_string(bad - 1));
+    }
+
+    // ---- parse: record counts per segment, then metadata
+    d_counts.ensure((size_t)(nseg + 1) * 16);
+    d_rec_base.ensure((size_t)(nseg + 2) * 8);
+    std::vector<uint64_t> counts(2 * (size_t)nseg + 2, 0), rec_base(nseg + 1, 0);
+    bool fixed_ok = false;
+    if (nseg && fixed_klen + fixed_vlen > 0) {
+      // candidate: every body is exactly k records of the fixed framing + EOF markers
+      const uint32_t rs = vint_size_u32(fixed_klen) + vint_size_u32(fixed_vlen) + fixed_klen + fixed_vlen;
+      fixed_ok = true;
+      for (uint32_t s = 0; s < nseg && fixed_ok; s++) {
+        uint64_t body = segs[s].body_end - segs[s].body0;
+        fixed_ok = body >= 2 && (body - 2) % rs == 0;
+        counts[s] = fixed_ok ? (body - 2) / rs : 0;
+        counts[nseg + s] = counts[s] * (fixed_klen + fixed_vlen);
+      }
+    }
+    ParseArrays pa{nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (nseg && !fixed_ok) {
+      k_parse_segments<false><<<(uint32_t)div_up(nseg, 64), 64, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, d_counts.as<uint64_t>(),
+                                                                       d_counts.as<uint64_t>() + nseg, nullptr, pa, d_bad);
+      launches++;
+      TG_CUDA(cudaGetLastError());
+      int bad = 0;
+      TG_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, (size_t)nseg * 16, cudaMemcpyDeviceToHost, st));
+      TG_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+      TG_CUDA(cudaStreamSynchronize(st));
+      TG_CHECK(bad == 0, TEZGPU_E_FORMAT, "malformed IFile segment " + std::to_string(bad - 1));
+    }
+    n = 0;
+    kv_bytes = 0;
+    for (uint32_t s = 0; s < nseg; s++) { rec_base[s] = n; n += counts[s]; kv_bytes += counts[nseg + s]; }
+    rec_base[nseg] = n;
+    TG_CHECK(n <= RADIX_MAX_N, TEZGPU_E_INVALID, "more than 2^30-1 records in one merge");
+    TG_CUDA(cudaMemcpyAsync(d_rec_base.p, rec_base.data(), (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, st));
+    d_koff.ensure((size_t)(n ? n : 1) * 8); d_voff.ensure((size_t)(n ? n : 1) * 8);
+    d_klen.ensure((size_t)(n ? n : 1) * 4); d_vlen.ensure((size_t)(n ? n : 1) * 4); d_tag.ensure((size_t)(n ? n : 1) * 4);
+    pa = ParseArrays{d_koff.as<uint64_t>(), d_voff.as<uint64_t>(), d_klen.as<uint32_t>(), d_vlen.as<uint32_t>(), d_tag.as<uint32_t>()};
+    if (n && fixed_ok) {
+      const uint32_t hl = vint_size_u32(fixed_klen) + vint_size_u32(fixed_vlen);
+      uint64_t hb = 0;
+      int b = 0;
+      for (int i = 0; i < vint_size_u32(fixed_klen); i++) hb |= (uint64_t)vint_byte_u32(fixed_klen, i) << (8 * b++);
+      for (int i = 0; i < vint_size_u32(fixed_vlen); i++) hb |= (uint64_t)vint_byte_u32(fixed_vlen, i) << (8 * b++);
+      k_parse_fixed_check<<<(uint32_t)std::min<uint64_t>(div_up(n, 256), 148 * 16), 256, 0, st>>>(
+          data, d_segs.as<SegDesc>(), nseg, d_rec_base.as<uint64_t>(), fixed_klen, fixed_vlen, hl, hb, pa, pipe.d_error() + 1);
+      launches++;
+      int mism = 0;
+      TG_CUDA(cudaMemcpyAsync(&mism, pipe.d_error() + 1, 4, cudaMemcpyDeviceToHost, st));
+      TG_CUDA(cudaStreamSynchronize(st));
+      if (mism) {
+        // not the fixed framing after all (e.g. run-length encoded input): take the general walk
+        fixed_klen = fixed_vlen = 0;
+        open_general_reparse(nseg, counts, rec_base);
+        pa = ParseArrays{d_koff.as<uint64_t>(), d_voff.as<uint64_t>(), d_klen.as<uint32_t>(), d_vlen.as<uint32_t>(), d_tag.as<uint32_t>()};
+      }
+    } else if (n) {
+      k_parse_segments<true><<<(uint32_t)div_up(nseg, 64), 64, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, nullptr, nullptr,
+                                                                      d_rec_base.as<uint64_t>(), pa, d_bad);
+      launches++;
+    }
+    TG_CUDA(cudaGetLastError());
+
+    // ---- merge = stable sort of the union of the runs by the RawComparator
+    Records r;
+    memset(&r, 0, sizeof(r));
+    r.kv = data;
+    r.kv_bytes = align_up(seg_bytes, 16) + 32;
+    r.key_off = d_koff.as<uint64_t>();
+    r.val_off = d_voff.as<uint64_t>();
+    r.key_len = d_klen.as<uint32_t>();
+    r.val_len = d_vlen.as<uint32_t>();
+    r.tag = d_tag.as<uint32_t>();
+    r.partition = nullptr;
+    r.n = (uint32_t)n;
+    r.fixed = 0;
+    pipe.sort_phase(r);
+    launches += pipe.state.launches;
+    cursor = 0;
+    have_kvoff = false;
+  }
+
+  void open_general_reparse(uint32_t nseg, std::vector<uint64_t> &counts, std::vector<uint64_t> &rec_base) {
+    cudaStream_t st = pipe.stream;
+    int *d_bad = pipe.d_error();
+    ParseArrays pa{nullptr, nullptr, nullptr, nullptr, nullptr};
+    k_parse_segments<false><<<(uint32_t)div_up(nseg, 64), 64, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, d_counts.as<uint64_t>(),
+                                                                     d_counts.as<uint64_t>() + nseg, nullptr, pa, d_bad);
+    int bad = 0;
+    TG_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, (size_t)nseg * 16, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaStreamSynchronize(st));
+    TG_CHECK(bad == 0, TEZGPU_E_FORMAT, "malformed IFile segment " + std::to_string(bad - 1));
+    n = 0;
+    kv_bytes = 0;
+    for (uint32_t s = 0; s < nseg; s++) { rec_base[s] = n; n += counts[s]; kv_bytes += counts[nseg + s]; }
+    rec_base[nseg] = n;
+    TG_CHECK(n <= RADIX_MAX_N, TEZGPU_E_INVALID, "more than 2^30-1 records in one merge");
+    TG_CUDA(cudaMemcpyAsync(d_rec_base.p, rec_base.data(), (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, st));
+    d_koff.ensure((size_t)(n ? n : 1) * 8); d_voff.ensure((size_t)(n ? n : 1) * 8);
+    d_klen.ensure((size_t)(n ? n : 1) * 4); d_vlen.ensure((size_t)(n ? n : 1) * 4); d_tag.ensure((size_t)(n ? n : 1) * 4);
+    pa = ParseArrays{d_koff.as<uint64_t>(), d_voff.as<uint64_t>(), d_klen.as<uint32_t>(), d_vlen.as<uint32_t>(), d_tag.as<uint32_t>()};
+    if (n) k_parse_segments<true><<<(uint32_t)div_up(nseg, 64), 64, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, nullptr, nullptr,
+                                                                            d_rec_base.as<uint64_t>(), pa, d_bad);
+    launches += 2;
+  }
+
+  uint64_t output_bound() const { return SortPipeline::output_bound(n, kv_bytes, 1) + 16; }
+
+  // TezMerger.writeFile: one IFile segment, equal adjacent keys written through IFile.REPEAT_KEY
+  void write_device(uint8_t *d_out_buf, uint64_t cap, int writer_rle, int64_t *raw_len, int64_t *part_len, tezgpu_stats *stats) {
+    int64_t index[3] = {0, 0, 0};
+    uint64_t len = 0;
+    tezgpu_stats st;
+    pipe.emit_phase(writer_rle ? 1 : 0, true, d_out_buf, cap, &len, index, &st);
+    st.output_bytes = (int64_t)kv_bytes;
+    st.kernel_launches += launches - pipe.state.launches;
+    if (raw_len) *raw_len = index[1];
+    if (part_len) *part_len = index[2];
+    if (stats) *stats = st;
+  }
+
+  void ensure_kvoff() {
+    if (have_kvoff) return;
+    cudaStream_t st = pipe.stream;
+    const uint32_t nn = (uint32_t)n;
+    d_sizes.ensure((size_t)(nn ? nn : 1) * 4);
+    d_kvoff.ensure(((size_t)nn + 2) * 8);
+    if (nn) {
+      const uint32_t nblk = (uint32_t)div_up(nn, SCAN_TILE);
+      pipe.blk.ensure(((size_t)nblk + 2) * 8);
+      k_kv_sizes<<<(uint32_t)div_up(nn, 256), 256, 0, st>>>(pipe.state.rec, pipe.state.order, d_sizes.as<uint32_t>());
+      k_sum_u32_blocks<<<nblk, SCAN_THREADS, 0, st>>>(d_sizes.as<uint32_t>(), nn, pipe.blk.as<uint64_t>());
+      k_scan_block_sums<<<1, 1024, 0, st>>>(pipe.blk.as<uint64_t>(), nblk);
+      k_scan_u32_apply<<<nblk, SCAN_THREADS, 0, st>>>(d_sizes.as<uint32_t>(), nn, pipe.blk.as<uint64_t>(), d_kvoff.as<uint64_t>());
+      TG_CUDA(cudaGetLastError());
+    } else {
+      TG_CUDA(cudaMemsetAsync(d_kvoff.p, 0, 16, st));
+    }
+    have_kvoff = true;
+  }
+
+  // next()/getKey()/getValue()/isSameKey() in batches
+  void next_batch(uint8_t *out_kv, uint64_t cap, tezgpu_kv_index *idx, uint32_t idx_cap, uint32_t *count) {
+    TG_CUDA(cudaSetDevice(pipe.conf.device));
+    cudaStream_t st = pipe.stream;
+    *count = 0;
+    if (cursor >= n || idx_cap == 0) return;
+    ensure_kvoff();
+    uint32_t *d_cnt = pipe.d_large();
+    k_find_batch<<<1, 1, 0, st>>>(d_kvoff.as<uint64_t>(), (uint32_t)n, (uint32_t)cursor, idx_cap, cap, d_cnt);
+    uint32_t cnt = 0;
+    TG_CUDA(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaStreamSynchronize(st));
+    TG_CHECK(cnt > 0, TEZGPU_E_NOMEM, "batch buffer smaller than one record");
+    uint64_t ends[2];
+    TG_CUDA(cudaMemcpyAsync(&ends[0], d_kvoff.as<uint64_t>() + cursor, 8, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaMemcpyAsync(&ends[1], d_kvoff.as<uint64_t>() + cursor + cnt, 8, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaStreamSynchronize(st));
+    const uint64_t bytes = ends[1] - ends[0];
+    d_batch.ensure(bytes + 16);
+    d_batch_idx.ensure((size_t)cnt * sizeof(KvIndexDev));
+    k_gather_batch<<<(uint32_t)div_up((uint64_t)cnt * 32, 256), 256, 0, st>>>(pipe.state.rec, pipe.state.order, pipe.same.as<uint8_t>(),
+                                                                         d_kvoff.as<uint64_t>(), (uint32_t)cursor, cnt,
+                                                                         d_batch.as<uint8_t>(), d_batch_idx.as<KvIndexDev>());
+    TG_CUDA(cudaGetLastError());
+    if (bytes) TG_CUDA(cudaMemcpyAsync(out_kv, d_batch.p, bytes, cudaMemcpyDeviceToHost, st));
+    static_assert(sizeof(KvIndexDev) == sizeof(tezgpu_kv_index), "index layout");
+    TG_CUDA(cudaMemcpyAsync(idx, d_batch_idx.p, (size_t)cnt * sizeof(KvIndexDev), cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaStreamSynchronize(st));
+    cursor += cnt;
+    *count = cnt;
+  }
+};
+
+}  // namespace tezgpu

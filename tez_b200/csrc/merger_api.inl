@@ -1,11 +1,87 @@
-// merger_api.inl -- extern "C" merge entry points
+// merger_api.inl -- extern "C" merge entry points (include/tezgpu.h)
+struct tezgpu_merger {
+  Merger m;
+  explicit tezgpu_merger(const tezgpu_conf &c) : m(c) {}
+};
+
 extern "C" {
-int32_t tezgpu_merge_open(const tezgpu_conf *, const tezgpu_segment *, uint32_t, tezgpu_merger **) { g_last_error = "merge not built"; return TEZGPU_E_UNSUPPORTED; }
-int32_t tezgpu_merge_counts(tezgpu_merger *, uint64_t *, uint64_t *) { return TEZGPU_E_UNSUPPORTED; }
-int32_t tezgpu_merge_next_batch(tezgpu_merger *, uint8_t *, uint64_t, tezgpu_kv_index *, uint32_t, uint32_t *) { return TEZGPU_E_UNSUPPORTED; }
-int32_t tezgpu_merge_write_ifile(tezgpu_merger *, const char *, uint8_t *, uint64_t, int32_t, int64_t *, int64_t *, tezgpu_stats *) { return TEZGPU_E_UNSUPPORTED; }
-uint64_t tezgpu_merge_output_bound(const tezgpu_merger *) { return 0; }
-int32_t tezgpu_merge_write_ifile_device(tezgpu_merger *, void *, uint64_t, int32_t, int64_t *, int64_t *, tezgpu_stats *) { return TEZGPU_E_UNSUPPORTED; }
-void *tezgpu_merge_stream(tezgpu_merger *) { return nullptr; }
-int32_t tezgpu_merge_close(tezgpu_merger *) { return TEZGPU_OK; }
+
+int32_t tezgpu_merge_open(const tezgpu_conf *conf, const tezgpu_segment *segs, uint32_t nseg, tezgpu_merger **out) {
+  tezgpu_merger *h = nullptr;
+  try {
+    TG_CHECK(conf && out && (segs || nseg == 0), TEZGPU_E_INVALID, "null argument");
+    TG_CHECK(conf->abi_version == TEZGPU_ABI_VERSION, TEZGPU_E_INVALID, "tezgpu_conf.abi_version mismatch");
+    h = new tezgpu_merger(*conf);
+    h->m.open(segs, nseg);
+    *out = h;
+  } catch (const tezgpu::Error &e) {
+    delete h;
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::exception &e) {
+    delete h;
+    g_last_error = e.what();
+    return TEZGPU_E_INVALID;
+  }
+  return TEZGPU_OK;
 }
+
+int32_t tezgpu_merge_counts(tezgpu_merger *m, uint64_t *records, uint64_t *kv_bytes) {
+  TG_API_BEGIN
+  TG_CHECK(m, TEZGPU_E_INVALID, "null handle");
+  if (records) *records = m->m.n;
+  if (kv_bytes) *kv_bytes = m->m.kv_bytes;
+  TG_API_END
+}
+
+int32_t tezgpu_merge_next_batch(tezgpu_merger *m, uint8_t *out_kv, uint64_t cap, tezgpu_kv_index *idx, uint32_t idx_cap,
+                                uint32_t *n) {
+  TG_API_BEGIN
+  TG_CHECK(m && out_kv && idx && n, TEZGPU_E_INVALID, "null argument");
+  m->m.next_batch(out_kv, cap, idx, idx_cap, n);
+  TG_API_END
+}
+
+uint64_t tezgpu_merge_output_bound(const tezgpu_merger *m) { return m ? m->m.output_bound() : 0; }
+
+int32_t tezgpu_merge_write_ifile_device(tezgpu_merger *m, void *d_out, uint64_t out_cap, int32_t rle, int64_t *raw_len,
+                                        int64_t *part_len, tezgpu_stats *stats) {
+  TG_API_BEGIN
+  TG_CHECK(m && d_out, TEZGPU_E_INVALID, "null argument");
+  m->m.write_device((uint8_t *)d_out, out_cap, rle, raw_len, part_len, stats);
+  TG_API_END
+}
+
+int32_t tezgpu_merge_write_ifile(tezgpu_merger *m, const char *path, uint8_t *out, uint64_t out_cap, int32_t rle,
+                                 int64_t *raw_len, int64_t *part_len, tezgpu_stats *stats) {
+  TG_API_BEGIN
+  TG_CHECK(m && (path || out), TEZGPU_E_INVALID, "null argument");
+  Merger &mm = m->m;
+  uint64_t bound = mm.output_bound();
+  mm.d_out.ensure(bound);
+  int64_t raw = 0, part = 0;
+  mm.write_device(mm.d_out.as<uint8_t>(), mm.d_out.cap, rle, &raw, &part, stats);
+  uint8_t *host = out;
+  if (!host) {
+    mm.h_out.ensure((size_t)part + 16);
+    host = mm.h_out.as<uint8_t>();
+  } else {
+    TG_CHECK((uint64_t)part <= out_cap, TEZGPU_E_NOMEM, "output buffer too small for the merged segment");
+  }
+  TG_CUDA(cudaMemcpyAsync(host, mm.d_out.p, (size_t)part, cudaMemcpyDeviceToHost, mm.pipe.stream));
+  TG_CUDA(cudaStreamSynchronize(mm.pipe.stream));
+  if (path) write_file_0640(path, host, (size_t)part);
+  if (raw_len) *raw_len = raw;
+  if (part_len) *part_len = part;
+  TG_API_END
+}
+
+void *tezgpu_merge_stream(tezgpu_merger *m) { return m ? (void *)m->m.pipe.stream : nullptr; }
+
+int32_t tezgpu_merge_close(tezgpu_merger *m) {
+  TG_API_BEGIN
+  delete m;
+  TG_API_END
+}
+
+}  // extern "C"

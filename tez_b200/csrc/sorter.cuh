@@ -96,22 +96,39 @@ class SortPipeline {
   unsigned long long *d_dups() { return reinterpret_cast<unsigned long long *>(small.as<uint32_t>() + 2066); }
   uint64_t *d_totals() { return reinterpret_cast<uint64_t *>(small.as<uint32_t>() + 2068); }
 
+  // state left behind by sort_phase for emit_phase / the merger's record iterator
+  struct SortState {
+    Records rec;
+    uint32_t *K = nullptr;      // sorted sort words
+    uint32_t *order = nullptr;  // sorted position -> record index
+    uint64_t dup_count = 0, tie_records = 0;
+    int launches = 0;
+  } state;
+
   void run(Records rec, uint8_t *d_out, uint64_t out_cap, uint64_t *out_len, int64_t *index, tezgpu_stats *stats) {
+    sort_phase(rec);
+    int rle;
+    if (conf.rle_policy == TEZGPU_RLE_ON) rle = 1;
+    else if (conf.rle_policy == TEZGPU_RLE_OFF) rle = 0;
+    else rle = (conf.sorter_impl == 1) ? 0 : ((double)state.dup_count > 0.1 * (double)rec.n);
+    emit_phase(rle, false, d_out, out_cap, out_len, index, stats);
+  }
+
+  // partition + sort: stage, radix sort of (sort word, index), tie refinement.  Leaves K / order / same / counts.
+  void sort_phase(Records rec) {
     TG_CUDA(cudaSetDevice(conf.device));
     const uint32_t n = rec.n;
     const int P = conf.num_partitions;
     TG_CHECK(n <= RADIX_MAX_N, TEZGPU_E_INVALID, "more than 2^30-1 records in one sort");
-    TG_CHECK(((uintptr_t)d_out & 15u) == 0, TEZGPU_E_INVALID, "output buffer must be 16-byte aligned");
     rec.cmp = conf.comparator;
     rec.hash_partition = conf.partitioner == TEZGPU_PART_HASH;
     rec.num_partitions = P;
     rec.pbits = pbits;
-    TG_CHECK(rec.hash_partition || rec.partition || n == 0, TEZGPU_E_INVALID, "partition ids required (partitioner=GIVEN)");
+    TG_CHECK(rec.hash_partition || rec.partition || n == 0 || P == 1, TEZGPU_E_INVALID, "partition ids required (partitioner=GIVEN)");
     int launches = 0;
     timer.reset();
     timer.mark(stream);
 
-    const CrcTables *d_crc = DeviceConstants::get(conf.device).d_crc;
     const size_t n4 = (size_t)(n ? n : 1) * 4;
     keysA.ensure(n4); keysB.ensure(n4); valsA.ensure(n4); valsB.ensure(n4);
     same.ensure(n ? n : 1);
@@ -235,12 +252,31 @@ class SortPipeline {
       }
     }
     timer.mark(stream);
+    state.rec = rec;
+    state.K = K;
+    state.order = order;
+    state.dup_count = dup_count;
+    state.tie_records = tie_records;
+    state.launches = launches;
+  }
 
-    // ---------------- RLE decision (SORT/PipelinedSorter.java:1436-1438; see DESIGN.md for the AUTO rule)
-    int rle;
-    if (conf.rle_policy == TEZGPU_RLE_ON) rle = 1;
-    else if (conf.rle_policy == TEZGPU_RLE_OFF) rle = 0;
-    else rle = (conf.sorter_impl == 1) ? 0 : ((double)dup_count > 0.1 * (double)n);
+  // layout + emit of the sorted records as IFile segments.  merge_mode: REPEAT_KEY semantics of TezMerger.writeFile
+  // (empty keys may be run-length encoded too, SORT/TezMerger.java:215-245).
+  void emit_phase(int rle, bool merge_mode, uint8_t *d_out, uint64_t out_cap, uint64_t *out_len, int64_t *index,
+                  tezgpu_stats *stats) {
+    TG_CUDA(cudaSetDevice(conf.device));
+    TG_CHECK(((uintptr_t)d_out & 15u) == 0, TEZGPU_E_INVALID, "output buffer must be 16-byte aligned");
+    const Records rec = state.rec;
+    const uint32_t n = rec.n;
+    const int P = conf.num_partitions;
+    uint32_t *K = state.K, *order = state.order;
+    const uint64_t dup_count = state.dup_count, tie_records = state.tie_records;
+    int launches = state.launches;
+    const CrcTables *d_crc = DeviceConstants::get(conf.device).d_crc;
+    const size_t n4 = (size_t)(n ? n : 1) * 4;
+    const uint32_t nblk = (uint32_t)div_up(n ? n : 1, SCAN_TILE);
+    TG_CUDA(cudaMemsetAsync(seg_crc.p, 0, (size_t)P * 4, stream));
+    if (timer.n > (n ? 4 : 2)) timer.n = n ? 4 : 2;  // re-emit: drop the marks of a previous emit
 
     // ---------------- layout + emit
     EmitParams e;
@@ -256,7 +292,9 @@ class SortPipeline {
     e.crc = d_crc;
     e.rle = rle;
     e.send_empty = conf.send_empty_partition_details;
+    e.merge_mode = merge_mode ? 1 : 0;
     e.P = P;
+    k_part_bounds<<<(uint32_t)div_up((uint64_t)P + 1, 256), 256, 0, stream>>>(K, n, P, pbits, part_start.as<uint32_t>());
     const bool fixed_emit = rec.fixed && (!rle || dup_count == 0);
     uint64_t bound = output_bound(n, rec.fixed ? (uint64_t)n * (rec.klen + rec.vlen) : rec.kv_bytes, P);
     if (fixed_emit) {
@@ -284,7 +322,6 @@ class SortPipeline {
       }
       e.rec_off = rec_off.as<uint64_t>();
     }
-    k_part_bounds<<<(uint32_t)div_up((uint64_t)P + 1, 256), 256, 0, stream>>>(K, n, P, pbits, part_start.as<uint32_t>());
     k_layout<<<1, 1024, 0, stream>>>(e, seg_start.as<uint64_t>(), tile_start.as<uint32_t>(), d_index.as<int64_t>(), d_totals());
     launches += 2;
     TG_CUDA(cudaGetLastError());

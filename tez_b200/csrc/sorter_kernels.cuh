@@ -16,9 +16,11 @@ struct Records {
   const uint8_t *kv;        // serialized bytes, key immediately followed by value
   uint64_t kv_bytes;        // valid bytes in kv (multiple of 16 allocated)
   const uint64_t *key_off;  // var mode
+  const uint64_t *val_off;  // optional: value bytes not adjacent to the key (parsed IFile segments with repeats)
   const uint32_t *key_len;
   const uint32_t *val_len;
   const int32_t *partition;  // optional
+  const uint32_t *tag;       // merge only: (segment id << 1) | record was run-length encoded in its input segment
   uint32_t n;
   uint32_t klen, vlen;  // fixed mode
   int fixed;
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(256) k_stage(Records r, uint32_t *__restrict__
         for (int k = 0; k < 16; k++) h = 31u * h + (uint32_t)(int32_t)(int8_t)((w[k >> 2] >> (8 * (k & 3))) & 0xFF);
         p = (int32_t)((h & 0x7fffffffu) % (uint32_t)r.num_partitions);
       } else {
-        p = r.partition[i];
+        p = r.partition ? r.partition[i] : 0;
       }
     } else {
       uint64_t koff;
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(256) k_stage(Records r, uint32_t *__restrict__
 #pragma unroll
       for (uint32_t b = 0; b < 4; b++) prefix = (prefix << 8) | (b < clen ? norm_byte(r.cmp, content, b) : 0u);
       p = r.hash_partition ? (int32_t)((uint32_t)(key_hash_dev(r.cmp, key, klen) & 0x7fffffff) % (uint32_t)r.num_partitions)
-                           : r.partition[i];
+                           : (r.partition ? r.partition[i] : 0);
     }
     if (p < 0 || p >= r.num_partitions) {
       *error_flag = 1;  // "Illegal partition" (PipelinedSorter.java:410-413)
@@ -393,9 +395,29 @@ struct EmitParams {
   uint8_t fixed_hdr[12];       // fixed mode: vint(klen) vint(vlen)
   uint32_t fixed_hdr_len;
   int rle;
+  int merge_mode;      // TezMerger.writeFile semantics: isSameKey() records go through IFile.REPEAT_KEY
   int send_empty;
   int P;
 };
+
+// Is the record at sorted position r written as a repeat of the previous key ([RLE_MARKER] vint(vlen) value)?
+//  sorter: IFile.Writer(rle) compares the raw key bytes with the previous key and never fires for empty keys
+//          (SORT/IFile.java:541-544);
+//  merger: TezMerger.writeFile passes IFile.REPEAT_KEY when MergeQueue.isSameKey() -- the record was read as SAME_KEY
+//          from its own segment, or the top segment changed and the comparator reports equality
+//          (SORT/TezMerger.java:215-245,597-652) -- and the writer's own test applies on top when it was built with rle.
+__device__ __forceinline__ bool emit_is_repeat(const EmitParams &e, uint32_t r, uint32_t ps) {
+  if (r == ps || !e.same[r]) return false;
+  const Records &rec = e.rec;
+  const uint32_t i = e.order[r];
+  uint64_t koff;
+  uint32_t klen, vlen;
+  record_lookup(rec, i, koff, klen, vlen);
+  const bool writer = e.rle && klen > 0;
+  if (!e.merge_mode) return writer;
+  const uint32_t tag = rec.tag[i], tagp = rec.tag[e.order[r - 1]];
+  return writer || (tag & 1u) || ((tag >> 1) != (tagp >> 1));
+}
 
 // var mode: emitted size of the record at sorted position r (IFile.Writer.writeKVPair / writeValue / markers,
 // SORT/IFile.java:559-614): a repeated key costs [RLE_MARKER once] vint(vlen) val, the first new key after a run
@@ -408,20 +430,11 @@ __global__ void __launch_bounds__(256) k_emit_sizes(EmitParams e, const uint32_t
   uint32_t klen, vlen;
   record_lookup(rec, e.order[r], koff, klen, vlen);
   const int sh = 32 - rec.pbits;
-  uint32_t p = rec.pbits ? (K[r] >> sh) : 0;
-  bool first = (r == 0) || (rec.pbits && (K[r - 1] >> sh) != p);
-  bool last = (r + 1 == rec.n) || (rec.pbits && (K[r + 1] >> sh) != p);
-  bool same_r = e.rle && !first && e.same[r] && klen > 0;  // the writer's own test never fires for empty keys (:543)
-  bool same_prev = false;
-  if (e.rle && !first && r > 0) {
-    // previous record was written as a repeat?
-    bool first_prev = (r - 1 == 0) || (rec.pbits && (K[r - 2] >> sh) != p);
-    if (!first_prev && e.same[r - 1]) {
-      uint64_t ko2; uint32_t kl2, vl2;
-      record_lookup(rec, e.order[r - 1], ko2, kl2, vl2);
-      same_prev = kl2 > 0;
-    }
-  }
+  const uint32_t p = rec.pbits ? (K[r] >> sh) : 0;
+  const uint32_t ps = e.part_start[p], pe = e.part_start[p + 1];
+  const bool last = (r + 1 == pe);
+  const bool same_r = emit_is_repeat(e, r, ps);
+  const bool same_prev = (r > ps) && emit_is_repeat(e, r - 1, ps);
   uint32_t sz;
   if (same_r) sz = (same_prev ? 0u : 1u) + vint_size_u32(vlen) + vlen;
   else sz = (same_prev ? 1u : 0u) + vint_size_u32(klen) + vint_size_u32(vlen) + klen + vlen;
@@ -501,7 +514,9 @@ constexpr int EMIT_CRC_STRIDE_WORDS = EMIT_THREADS;
 
 struct EmitEntry {      // one record (or the header / EOF pseudo record) of a tile
   uint64_t src;         // offset in kv of the source bytes that follow the framing bytes
+  uint64_t src2;        // second source range (value bytes when they are not adjacent to the key)
   uint32_t src_len;
+  uint32_t src2_len;
   uint8_t hdr[12];      // framing bytes: [V_END] [RLE] vint(klen) vint(vlen)   or 'TIF\0' / EOF markers
   uint8_t hdr_len;
   uint8_t tail_fd;      // V_END_MARKER closing a run that ends the segment
@@ -603,7 +618,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(EmitParams e) {
   const uint64_t body0 = FIXED ? (uint64_t)(r0 - ps) * e.rec_size : (e.rec_off[r0] - e.rec_off[ps]);
   for (uint32_t j = tid; j < nr + 2; j += EMIT_THREADS) {
     EmitEntry en;
-    en.src = 0; en.src_len = 0; en.hdr_len = 0; en.tail_fd = 0;
+    en.src = 0; en.src_len = 0; en.src2 = 0; en.src2_len = 0; en.hdr_len = 0; en.tail_fd = 0;
     uint64_t loc;
     if (j == 0) {
       loc = 0;
@@ -625,20 +640,15 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(EmitParams e) {
         en.src_len = klen + vlen;
       } else {
         loc = (first_tile ? 4 : 0) + (e.rec_off[r] - e.rec_off[ps]) - body0;
-        bool first = (r == ps), last = (r + 1 == pe);
-        bool same_r = e.rle && !first && e.same[r] && klen > 0;
-        bool same_prev = false;
-        if (e.rle && !first && r - 1 != ps && e.same[r - 1]) {
-          uint64_t ko2; uint32_t kl2, vl2;
-          record_lookup(rec, e.order[r - 1], ko2, kl2, vl2);
-          same_prev = kl2 > 0;
-        }
+        const bool last = (r + 1 == pe);
+        const bool same_r = emit_is_repeat(e, r, ps);
+        const bool same_prev = (r > ps) && emit_is_repeat(e, r - 1, ps);
         uint32_t h = 0;
         if (same_r) {
           if (!same_prev) en.hdr[h++] = 0xFE;  // RLE_MARKER
           int s = vint_size_u32(vlen);
           for (int b = 0; b < s; b++) en.hdr[h++] = vint_byte_u32(vlen, b);
-          en.src = koff + klen;
+          en.src = rec.val_off ? rec.val_off[e.order[r]] : koff + klen;
           en.src_len = vlen;
           en.tail_fd = last ? 1 : 0;
         } else {
@@ -648,7 +658,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(EmitParams e) {
           s = vint_size_u32(vlen);
           for (int b = 0; b < s; b++) en.hdr[h++] = vint_byte_u32(vlen, b);
           en.src = koff;
-          en.src_len = klen + vlen;
+          if (rec.val_off) { en.src_len = klen; en.src2 = rec.val_off[e.order[r]]; en.src2_len = vlen; }
+          else en.src_len = klen + vlen;
         }
         en.hdr_len = (uint8_t)h;
       }
@@ -706,6 +717,11 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(EmitParams e) {
         if (left && y < en.hdr_len + en.src_len) {
           uint32_t take = min(left, en.hdr_len + en.src_len - y);
           merge_bytes(acc, kv_lo + en.src + (y - en.hdr_len), q, take, kv_lo, kv_hi);
+          y += take; q += take; left -= take;
+        }
+        if (left && y < en.hdr_len + en.src_len + en.src2_len) {
+          uint32_t take = min(left, en.hdr_len + en.src_len + en.src2_len - y);
+          merge_bytes(acc, kv_lo + en.src2 + (y - en.hdr_len - en.src_len), q, take, kv_lo, kv_hi);
           y += take; q += take; left -= take;
         }
         if (left) { put_byte(acc, q, 0xFDu); q++; left--; }  // closing V_END_MARKER

@@ -115,10 +115,10 @@ class GpuSorter:
 
 
 class GpuMerger:
-    def __init__(self, segments, comparator=CMP_BYTES, device=0, has_header=True, device_ptrs=False):
+    def __init__(self, segments, comparator=CMP_BYTES, device=0, has_header=True, device_ptrs=False, fixed=None):
         """segments: list of bytes / uint8 arrays (host) or (ptr, len) tuples when device_ptrs."""
         self.L = _lib.load()
-        self.conf = make_conf(1, comparator=comparator, partitioner=PART_GIVEN, device=device)
+        self.conf = make_conf(1, comparator=comparator, partitioner=PART_GIVEN, device=device, fixed=fixed)
         self._keep = []
         arr = (Segment * max(1, len(segments)))()
         flags = (SEG_HAS_HEADER if has_header else 0) | (SEG_DEVICE if device_ptrs else 0)
