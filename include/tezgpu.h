@@ -149,7 +149,7 @@ typedef struct tezgpu_segment {
   const void *data;
   uint64_t len;
   uint32_t flags;
-  uint32_t reserved;
+  uint32_t partition;              /* output partition this segment belongs to (0 for a single-partition merge) */
 } tezgpu_segment;
 
 /* one merged record: offsets into the batch buffer returned by tezgpu_merge_next_batch */
@@ -174,6 +174,10 @@ uint64_t tezgpu_merge_output_bound(const tezgpu_merger *m);
 /* device-resident output of the merged IFile segment (multi-GPU reduce side, bench) */
 int32_t tezgpu_merge_write_ifile_device(tezgpu_merger *m, void *d_out, uint64_t out_cap, int32_t rle, int64_t *raw_len,
                                         int64_t *part_len, tezgpu_stats *stats);
+/* Batched reduce side (multi-GPU shuffle): the merger was opened with conf.num_partitions = P and every segment
+ * names its partition; writes the P merged segments back to back like a file.out and fills index[3*P]. */
+int32_t tezgpu_merge_write_partitions_device(tezgpu_merger *m, void *d_out, uint64_t out_cap, int32_t rle,
+                                             uint64_t *out_len, int64_t *index, tezgpu_stats *stats);
 void *tezgpu_merge_stream(tezgpu_merger *m);
 int32_t tezgpu_merge_close(tezgpu_merger *m);
 

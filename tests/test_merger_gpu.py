@@ -146,3 +146,36 @@ def test_empty_inputs():
     assert recs == [] and seg == empty
     recs, seg = _gpu_merge([], T.CMP_BYTES)
     assert recs == [] and seg == empty
+
+
+def test_batched_multi_partition_merge_matches_per_partition_oracle():
+    """Reduce side of the multi-GPU shuffle: segments of several partitions from several producers, one device pass."""
+    import torch
+    P, G = 6, 3
+    outs = []
+    for g in range(G):
+        kv = O.gen_c2(g * 50000, 30000, seed=4)
+        r = O.pipelined_sort_fixed(O.sorter_conf(P), kv, 16, 64)
+        outs.append(r)
+    segs, parts = [], []
+    for g in range(G):
+        for p in range(P):
+            start, raw, part = (int(x) for x in outs[g]["index"][p])
+            if part:
+                segs.append(outs[g]["file_out"][start:start + part])
+                parts.append(p)
+    for fixed in ((16, 64), None):
+        with T.GpuMerger(segs, comparator=T.CMP_BYTES, partitions=parts, num_partitions=P, fixed=fixed) as m:
+            cap = m.output_bound()
+            d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+            n, index, st = m.write_partitions_device(d_out.data_ptr(), cap)
+            out = d_out[:n].cpu().numpy().tobytes()
+        off = 0
+        for p in range(P):
+            mine = [s for s, q in zip(segs, parts) if q == p]
+            exp = O.merge(mine, O.CMP_BYTES, factor=100)["ifile"]
+            start, raw, part = (int(x) for x in index[p])
+            assert start == off and part == len(exp)
+            assert out[start:start + part] == exp
+            off += part
+        assert off == n

@@ -27,7 +27,7 @@ class Stats(C.Structure):
 
 
 class Segment(C.Structure):
-    _fields_ = [("data", C.c_void_p), ("len", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+    _fields_ = [("data", C.c_void_p), ("len", C.c_uint64), ("flags", C.c_uint32), ("partition", C.c_uint32)]
 
 
 class KvIndex(C.Structure):
@@ -58,6 +58,7 @@ SYMBOLS = [
     ("tezgpu_merge_write_ifile", C.c_int32, [_V, C.c_char_p, _V, C.c_uint64, C.c_int32, _P(C.c_int64), _P(C.c_int64), _P(Stats)]),
     ("tezgpu_merge_output_bound", C.c_uint64, [_V]),
     ("tezgpu_merge_write_ifile_device", C.c_int32, [_V, _V, C.c_uint64, C.c_int32, _P(C.c_int64), _P(C.c_int64), _P(Stats)]),
+    ("tezgpu_merge_write_partitions_device", C.c_int32, [_V, _V, C.c_uint64, C.c_int32, _P(C.c_uint64), _V, _P(Stats)]),
     ("tezgpu_merge_stream", _V, [_V]),
     ("tezgpu_merge_close", C.c_int32, [_V]),
 ]

@@ -118,10 +118,11 @@ struct FastEmitParams {
   uint32_t stride;
 };
 
-template <int UNROLL>
+template <int UNROLL, bool ALIGNED>
 __global__ void __launch_bounds__(FE_THREADS) k_emit_fast(FastEmitParams fp) {
   __shared__ __align__(16) uint8_t s_img[FE_IMG_BYTES];
   __shared__ uint32_t s_idx[FE_MAX_RECS];
+  __shared__ uint64_t s_off[ALIGNED ? 1 : FE_MAX_RECS];  // source offsets of the tile's records (explicit-offset mode)
   __shared__ uint32_t s_tab[4 * 256];    // slice-by-4 tables
   __shared__ uint32_t s_adv[4 * 256];    // * x^(32*FE_THREADS)
   __shared__ uint32_t s_adv32[4 * 256];  // * x^(32*32)
@@ -145,7 +146,11 @@ __global__ void __launch_bounds__(FE_THREADS) k_emit_fast(FastEmitParams fp) {
     const uint32_t nr = td.nr;
     const bool first_tile = td.flags & 1u, last_tile = td.flags & 2u;
     __syncthreads();  // previous tile fully written out; tables loaded
-    if ((uint32_t)tid < nr) s_idx[tid] = e.order[td.r0 + tid];
+    if ((uint32_t)tid < nr) {
+      const uint32_t ri = e.order[td.r0 + tid];
+      s_idx[tid] = ri;
+      if (!ALIGNED) s_off[tid] = e.rec.key_off ? e.rec.key_off[ri] : (uint64_t)ri * stride;
+    }
     const uint64_t abs0 = td.abs0;
     const uint32_t lead = (uint32_t)(abs0 & 15u);
     const uint32_t rec0 = lead + (first_tile ? 4u : 0u);            // image offset of the first record
@@ -163,7 +168,27 @@ __global__ void __launch_bounds__(FE_THREADS) k_emit_fast(FastEmitParams fp) {
         if (q < npieces) {
           uint32_t j = fp.cpr == 1 ? q : __umulhi(q, fp.cpr_magic);
           uint32_t c = q - j * fp.cpr;
-          v[u] = ldg_stream_v4(kv + (uint64_t)s_idx[j] * stride + 16u * c);
+          if (ALIGNED) {
+            v[u] = ldg_stream_v4(kv + (uint64_t)s_idx[j] * stride + 16u * c);
+          } else {
+            // records at arbitrary byte offsets (parsed IFile segments): two aligned 128-bit loads + funnel shift;
+            // the neighbouring lane's loads hit the same lines in L1
+            const uint8_t *a = kv + s_off[j] + 16u * c;
+            const uint32_t sh = (uint32_t)((uintptr_t)a & 15u);
+            const uint4 *pa = reinterpret_cast<const uint4 *>(a - sh);
+            uint4 lo4 = __ldg(pa);
+            uint4 hi4 = sh ? __ldg(pa + 1) : lo4;
+            const uint32_t bsh = (sh & 3u) * 8u;
+            uint32_t w0, w1, w2, w3, w4;
+            switch (sh >> 2) {
+              case 0: w0 = lo4.x; w1 = lo4.y; w2 = lo4.z; w3 = lo4.w; w4 = hi4.x; break;
+              case 1: w0 = lo4.y; w1 = lo4.z; w2 = lo4.w; w3 = hi4.x; w4 = hi4.y; break;
+              case 2: w0 = lo4.z; w1 = lo4.w; w2 = hi4.x; w3 = hi4.y; w4 = hi4.z; break;
+              default: w0 = lo4.w; w1 = hi4.x; w2 = hi4.y; w3 = hi4.z; w4 = hi4.w; break;
+            }
+            v[u] = make_uint4(__funnelshift_r(w0, w1, bsh), __funnelshift_r(w1, w2, bsh), __funnelshift_r(w2, w3, bsh),
+                              __funnelshift_r(w3, w4, bsh));
+          }
           dst[u] = img_base + rec0 + j * rec_size + hdr_len + 16u * c;
         }
       }

@@ -17,7 +17,7 @@ struct SegDesc {
   uint64_t body0;     // offset of the first body byte inside the segment (4 with header, 0 in-memory)
   uint64_t body_end;  // offset just past the EOF markers' possible position: len - 4 (checksum / slack excluded)
   uint32_t has_header;
-  uint32_t pad;
+  uint32_t partition;
 };
 
 // ------------------------------------------------------------------------------------------------ checksum
@@ -120,6 +120,7 @@ struct ParseArrays {
   uint32_t *key_len;
   uint32_t *val_len;
   uint32_t *tag;  // (segment << 1) | read as SAME_KEY (run-length encoded in the input)
+  int32_t *partition;
 };
 
 // Walks one segment with IFile.Reader semantics (positionToNextRecord / readRawKey / nextRawValue,
@@ -165,6 +166,7 @@ __global__ void k_parse_segments(const uint8_t *__restrict__ data, const SegDesc
       out.key_len[base + n] = (uint32_t)orig_klen;
       out.val_len[base + n] = (uint32_t)cur_vlen;
       out.tag[base + n] = (s << 1) | (cur_klen == -2 ? 1u : 0u);
+      out.partition[base + n] = (int32_t)sd.partition;
     }
     n++;
     bytes += (uint64_t)orig_klen + (uint64_t)cur_vlen;
@@ -199,6 +201,7 @@ __global__ void k_parse_fixed_check(const uint8_t *__restrict__ data, const SegD
     out.key_len[i] = klen;
     out.val_len[i] = vlen;
     out.tag[i] = lo << 1;
+    out.partition[i] = (int32_t)sd.partition;
   }
 }
 
@@ -258,7 +261,7 @@ class Merger {
  public:
   SortPipeline pipe;
   DeviceBuffer d_data, d_segs, d_piece_start, d_piece_crc, d_seg_crc, d_counts, d_rec_base;
-  DeviceBuffer d_koff, d_voff, d_klen, d_vlen, d_tag, d_sizes, d_kvoff, d_batch, d_batch_idx, d_out;
+  DeviceBuffer d_koff, d_voff, d_klen, d_vlen, d_tag, d_part, d_sizes, d_kvoff, d_batch, d_batch_idx, d_out;
   PinnedBuffer h_stage, h_out;
   std::vector<SegDesc> segs;
   uint64_t n = 0, kv_bytes = 0, seg_bytes = 0, cursor = 0;
@@ -267,13 +270,14 @@ class Merger {
   const uint8_t *data = nullptr;  // base of the segment bytes on the device
 
   static tezgpu_conf pipe_conf(tezgpu_conf c) {
-    c.num_partitions = 1;
+    if (c.num_partitions < 1) c.num_partitions = 1;
     c.partitioner = TEZGPU_PART_GIVEN;
-    c.send_empty_partition_details = 0;  // a merge always writes its (possibly empty) segment
+    if (c.num_partitions == 1) c.send_empty_partition_details = 0;  // a merge always writes its (possibly empty) segment
     c.fixed_key_len = c.fixed_val_len = 0;
     return c;
   }
   uint32_t fixed_klen = 0, fixed_vlen = 0;
+  bool parsed_fixed = false;
 
   explicit Merger(const tezgpu_conf &c) : pipe(pipe_conf(c)), fixed_klen(c.fixed_key_len), fixed_vlen(c.fixed_val_len) {}
 
@@ -292,7 +296,8 @@ class Merger {
       segs[s].body0 = hdr ? 4 : 0;
       segs[s].body_end = in[s].len - 4;
       segs[s].has_header = hdr ? 1 : 0;
-      segs[s].pad = 0;
+      segs[s].partition = in[s].partition;
+      TG_CHECK((int)in[s].partition < pipe.conf.num_partitions, TEZGPU_E_INVALID, "segment partition out of range");
       off = align_up(off + in[s].len, 16);
     }
     seg_bytes = off;
@@ -366,7 +371,7 @@ class Merger {
         counts[nseg + s] = counts[s] * (fixed_klen + fixed_vlen);
       }
     }
-    ParseArrays pa{nullptr, nullptr, nullptr, nullptr, nullptr};
+    ParseArrays pa{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (nseg && !fixed_ok) {
       k_parse_segments<false><<<(uint32_t)div_up(nseg, 64), 64, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, d_counts.as<uint64_t>(),
                                                                        d_counts.as<uint64_t>() + nseg, nullptr, pa, d_bad);
@@ -385,8 +390,8 @@ class Merger {
     TG_CHECK(n <= RADIX_MAX_N, TEZGPU_E_INVALID, "more than 2^30-1 records in one merge");
     TG_CUDA(cudaMemcpyAsync(d_rec_base.p, rec_base.data(), (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, st));
     d_koff.ensure((size_t)(n ? n : 1) * 8); d_voff.ensure((size_t)(n ? n : 1) * 8);
-    d_klen.ensure((size_t)(n ? n : 1) * 4); d_vlen.ensure((size_t)(n ? n : 1) * 4); d_tag.ensure((size_t)(n ? n : 1) * 4);
-    pa = ParseArrays{d_koff.as<uint64_t>(), d_voff.as<uint64_t>(), d_klen.as<uint32_t>(), d_vlen.as<uint32_t>(), d_tag.as<uint32_t>()};
+    d_klen.ensure((size_t)(n ? n : 1) * 4); d_vlen.ensure((size_t)(n ? n : 1) * 4); d_tag.ensure((size_t)(n ? n : 1) * 4); d_part.ensure((size_t)(n ? n : 1) * 4);
+    pa = ParseArrays{d_koff.as<uint64_t>(), d_voff.as<uint64_t>(), d_klen.as<uint32_t>(), d_vlen.as<uint32_t>(), d_tag.as<uint32_t>(), d_part.as<int32_t>()};
     if (n && fixed_ok) {
       const uint32_t hl = vint_size_u32(fixed_klen) + vint_size_u32(fixed_vlen);
       uint64_t hb = 0;
@@ -399,11 +404,11 @@ class Merger {
       int mism = 0;
       TG_CUDA(cudaMemcpyAsync(&mism, pipe.d_error() + 1, 4, cudaMemcpyDeviceToHost, st));
       TG_CUDA(cudaStreamSynchronize(st));
+      parsed_fixed = !mism;
       if (mism) {
         // not the fixed framing after all (e.g. run-length encoded input): take the general walk
-        fixed_klen = fixed_vlen = 0;
         open_general_reparse(nseg, counts, rec_base);
-        pa = ParseArrays{d_koff.as<uint64_t>(), d_voff.as<uint64_t>(), d_klen.as<uint32_t>(), d_vlen.as<uint32_t>(), d_tag.as<uint32_t>()};
+        pa = ParseArrays{d_koff.as<uint64_t>(), d_voff.as<uint64_t>(), d_klen.as<uint32_t>(), d_vlen.as<uint32_t>(), d_tag.as<uint32_t>(), d_part.as<int32_t>()};
       }
     } else if (n) {
       k_parse_segments<true><<<(uint32_t)div_up(nseg, 64), 64, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, nullptr, nullptr,
@@ -422,9 +427,14 @@ class Merger {
     r.key_len = d_klen.as<uint32_t>();
     r.val_len = d_vlen.as<uint32_t>();
     r.tag = d_tag.as<uint32_t>();
-    r.partition = nullptr;
+    r.partition = pipe.conf.num_partitions > 1 ? d_part.as<int32_t>() : nullptr;
     r.n = (uint32_t)n;
     r.fixed = 0;
+    if (parsed_fixed && n) {  // every segment had the fixed framing: constant sizes, explicit offsets
+      r.fixed = 1;
+      r.klen = fixed_klen;
+      r.vlen = fixed_vlen;
+    }
     pipe.sort_phase(r);
     launches += pipe.state.launches;
     cursor = 0;
@@ -434,7 +444,7 @@ class Merger {
   void open_general_reparse(uint32_t nseg, std::vector<uint64_t> &counts, std::vector<uint64_t> &rec_base) {
     cudaStream_t st = pipe.stream;
     int *d_bad = pipe.d_error();
-    ParseArrays pa{nullptr, nullptr, nullptr, nullptr, nullptr};
+    ParseArrays pa{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     k_parse_segments<false><<<(uint32_t)div_up(nseg, 64), 64, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, d_counts.as<uint64_t>(),
                                                                      d_counts.as<uint64_t>() + nseg, nullptr, pa, d_bad);
     int bad = 0;
@@ -449,14 +459,14 @@ class Merger {
     TG_CHECK(n <= RADIX_MAX_N, TEZGPU_E_INVALID, "more than 2^30-1 records in one merge");
     TG_CUDA(cudaMemcpyAsync(d_rec_base.p, rec_base.data(), (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, st));
     d_koff.ensure((size_t)(n ? n : 1) * 8); d_voff.ensure((size_t)(n ? n : 1) * 8);
-    d_klen.ensure((size_t)(n ? n : 1) * 4); d_vlen.ensure((size_t)(n ? n : 1) * 4); d_tag.ensure((size_t)(n ? n : 1) * 4);
-    pa = ParseArrays{d_koff.as<uint64_t>(), d_voff.as<uint64_t>(), d_klen.as<uint32_t>(), d_vlen.as<uint32_t>(), d_tag.as<uint32_t>()};
+    d_klen.ensure((size_t)(n ? n : 1) * 4); d_vlen.ensure((size_t)(n ? n : 1) * 4); d_tag.ensure((size_t)(n ? n : 1) * 4); d_part.ensure((size_t)(n ? n : 1) * 4);
+    pa = ParseArrays{d_koff.as<uint64_t>(), d_voff.as<uint64_t>(), d_klen.as<uint32_t>(), d_vlen.as<uint32_t>(), d_tag.as<uint32_t>(), d_part.as<int32_t>()};
     if (n) k_parse_segments<true><<<(uint32_t)div_up(nseg, 64), 64, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, nullptr, nullptr,
                                                                             d_rec_base.as<uint64_t>(), pa, d_bad);
     launches += 2;
   }
 
-  uint64_t output_bound() const { return SortPipeline::output_bound(n, kv_bytes, 1) + 16; }
+  uint64_t output_bound() const { return SortPipeline::output_bound(n, kv_bytes, pipe.conf.num_partitions) + 16; }
 
   // TezMerger.writeFile: one IFile segment, equal adjacent keys written through IFile.REPEAT_KEY
   void write_device(uint8_t *d_out_buf, uint64_t cap, int writer_rle, int64_t *raw_len, int64_t *part_len, tezgpu_stats *stats) {
@@ -468,6 +478,15 @@ class Merger {
     st.kernel_launches += launches - pipe.state.launches;
     if (raw_len) *raw_len = index[1];
     if (part_len) *part_len = index[2];
+    if (stats) *stats = st;
+  }
+
+  void write_partitions_device(uint8_t *d_out_buf, uint64_t cap, int writer_rle, uint64_t *out_len, int64_t *index,
+                               tezgpu_stats *stats) {
+    tezgpu_stats st;
+    pipe.emit_phase(writer_rle ? 1 : 0, true, d_out_buf, cap, out_len, index, &st);
+    st.output_bytes = (int64_t)kv_bytes;
+    st.kernel_launches += launches - pipe.state.launches;
     if (stats) *stats = st;
   }
 

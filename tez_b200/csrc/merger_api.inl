@@ -76,6 +76,14 @@ int32_t tezgpu_merge_write_ifile(tezgpu_merger *m, const char *path, uint8_t *ou
   TG_API_END
 }
 
+int32_t tezgpu_merge_write_partitions_device(tezgpu_merger *m, void *d_out, uint64_t out_cap, int32_t rle,
+                                             uint64_t *out_len, int64_t *index, tezgpu_stats *stats) {
+  TG_API_BEGIN
+  TG_CHECK(m && d_out, TEZGPU_E_INVALID, "null argument");
+  m->m.write_partitions_device((uint8_t *)d_out, out_cap, rle, out_len, index, stats);
+  TG_API_END
+}
+
 void *tezgpu_merge_stream(tezgpu_merger *m) { return m ? (void *)m->m.pipe.stream : nullptr; }
 
 int32_t tezgpu_merge_close(tezgpu_merger *m) {

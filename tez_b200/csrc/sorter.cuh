@@ -152,7 +152,7 @@ class SortPipeline {
     if (n) {
       // ---------------- stage
       TG_CUDA(cudaMemsetAsync(same.p, 0, n, stream));
-      const bool fast16 = rec.fixed && rec.klen == 16 && ((rec.klen + rec.vlen) % 16 == 0) && rec.cmp == CMP_BYTES &&
+      const bool fast16 = rec.fixed && !rec.key_off && rec.klen == 16 && ((rec.klen + rec.vlen) % 16 == 0) && rec.cmp == CMP_BYTES &&
                           (((uintptr_t)rec.kv & 15u) == 0);
       int sgrid = (int)std::min<uint64_t>(div_up(n, 256), 148 * 16);
       if (fast16) k_stage<true><<<sgrid, 256, 0, stream>>>(rec, K, d_hist(), d_error());
@@ -333,10 +333,11 @@ class SortPipeline {
     const uint64_t tiles = hs[1];
     TG_CHECK(file_bytes <= bound, TEZGPU_E_INVALID, "internal: output exceeds bound");
     TG_CHECK(file_bytes <= out_cap, TEZGPU_E_NOMEM, "output buffer too small for file.out");
-    // fixed-width records on a 16-byte stride take the source-oriented kernel (emit_fast.cuh)
+    // fixed-width records take the source-oriented kernel (emit_fast.cuh): 16-byte aligned packed records use one
+    // 128-bit load per piece, records at explicit / unaligned offsets two loads + a funnel shift
     const uint32_t stride = rec.klen + rec.vlen;
-    const bool fast_emit = fixed_emit && stride >= 16 && (stride % 16 == 0) && (((uintptr_t)rec.kv & 15u) == 0) &&
-                           !getenv("TEZGPU_NO_FAST_EMIT");
+    const bool fast_emit = fixed_emit && stride >= 16 && (stride % 16 == 0) && !getenv("TEZGPU_NO_FAST_EMIT");
+    const bool fast_aligned = fast_emit && !rec.key_off && (((uintptr_t)rec.kv & 15u) == 0);
     FastEmitParams fp;
     if (tiles && fast_emit) {
       tile_desc.ensure((size_t)tiles * sizeof(TileDesc));
@@ -355,9 +356,15 @@ class SortPipeline {
     if (tiles) {
       if (fast_emit) {
         int per_sm = 0;
-        TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_fast<5>, FE_THREADS, 0));
-        uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));
-        k_emit_fast<5><<<grid, FE_THREADS, 0, stream>>>(fp);
+        if (fast_aligned) {
+          TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_fast<5, true>, FE_THREADS, 0));
+          uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));
+          k_emit_fast<5, true><<<grid, FE_THREADS, 0, stream>>>(fp);
+        } else {
+          TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_fast<5, false>, FE_THREADS, 0));
+          uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));
+          k_emit_fast<5, false><<<grid, FE_THREADS, 0, stream>>>(fp);
+        }
         k_crc_combine<<<(uint32_t)div_up(tiles, 256), 256, 0, stream>>>(fp.tile_crc, (uint32_t)tiles, d_crc, seg_crc.as<uint32_t>());
         launches++;
       } else if (fixed_emit) k_emit<true><<<(uint32_t)tiles, EMIT_THREADS, 0, stream>>>(e);

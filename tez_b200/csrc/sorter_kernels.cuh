@@ -33,7 +33,8 @@ struct Records {
 __device__ __forceinline__ void record_lookup(const Records &r, uint32_t i, uint64_t &koff, uint32_t &klen,
                                               uint32_t &vlen) {
   if (r.fixed) {
-    koff = (uint64_t)i * (r.klen + r.vlen);
+    // fixed framing; key_off present = records live at explicit offsets (parsed fixed-width IFile segments)
+    koff = r.key_off ? r.key_off[i] : (uint64_t)i * (r.klen + r.vlen);
     klen = r.klen;
     vlen = r.vlen;
   } else {
@@ -648,7 +649,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(EmitParams e) {
           if (!same_prev) en.hdr[h++] = 0xFE;  // RLE_MARKER
           int s = vint_size_u32(vlen);
           for (int b = 0; b < s; b++) en.hdr[h++] = vint_byte_u32(vlen, b);
-          en.src = rec.val_off ? rec.val_off[e.order[r]] : koff + klen;
+          en.src = (rec.val_off && !rec.fixed) ? rec.val_off[e.order[r]] : koff + klen;
           en.src_len = vlen;
           en.tail_fd = last ? 1 : 0;
         } else {
@@ -658,7 +659,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(EmitParams e) {
           s = vint_size_u32(vlen);
           for (int b = 0; b < s; b++) en.hdr[h++] = vint_byte_u32(vlen, b);
           en.src = koff;
-          if (rec.val_off) { en.src_len = klen; en.src2 = rec.val_off[e.order[r]]; en.src2_len = vlen; }
+          if (rec.val_off && !rec.fixed) { en.src_len = klen; en.src2 = rec.val_off[e.order[r]]; en.src2_len = vlen; }
           else en.src_len = klen + vlen;
         }
         en.hdr_len = (uint8_t)h;

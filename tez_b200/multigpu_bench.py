@@ -1,5 +1,105 @@
-"""Multi-GPU arm of bench.py (filled in once the merge path is built)."""
+"""Multi-GPU arm of bench.py: BASELINE config 4 shape, weak scaling, one rank per GPU.
+
+step = local partition+sort (P partitions) -> all-to-all of the partition segments to their owners over NVLink
+       -> batched k-way merge of the G runs of every owned partition into the final segments.
+"""
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+KEY_LEN, VAL_LEN = 16, 64
+REC = KEY_LEN + VAL_LEN
+OUT_REC = REC + 2
 
 
-def run(args, *a):
-    raise SystemExit("multi-GPU bench not built yet")
+def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
+    import tez_b200 as T
+    from tez_b200 import shuffle, synth
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    n, P = args.records, 1024
+    d_kv = synth.gen_c2(rank * n, n, seed=4, device=dev)
+    sorter = T.GpuSorter(P, fixed=(KEY_LEN, VAL_LEN), device=local)
+    cap = n * OUT_REC + 10 * P + 4096
+    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    d_merged = torch.empty(int(cap * 1.3) + (1 << 20), dtype=torch.uint8, device=dev)
+    p0, p1 = shuffle.owner_ranges(P, world)[rank]
+    launches = [0]
+    phase_ms = {"sort": [], "exchange": [], "merge": []}
+
+    def step(timed):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record()
+        out_len, index, st = sorter.sort_device_fixed(d_kv.data_ptr(), n, d_out.data_ptr(), cap)
+        e[1].record()
+        recv, segs = shuffle.exchange_partitions(d_out[:out_len], index, P)
+        e[2].record()
+        base = recv.data_ptr()
+        m = T.GpuMerger([(base + off, ln) for off, ln, _, _ in segs], comparator=T.CMP_BYTES, device=local,
+                        device_ptrs=True, fixed=(KEY_LEN, VAL_LEN), partitions=[p for _, _, p, _ in segs],
+                        num_partitions=p1 - p0)
+        mlen, mindex, mst = m.write_partitions_device(d_merged.data_ptr(), d_merged.numel())
+        nrec, _ = m.counts()
+        m.close()
+        e[3].record()
+        if timed:
+            torch.cuda.synchronize()
+            launches[0] += st["kernel_launches"] + mst["kernel_launches"]
+            phase_ms["sort"].append(e[0].elapsed_time(e[1]))
+            phase_ms["exchange"].append(e[1].elapsed_time(e[2]))
+            phase_ms["merge"].append(e[2].elapsed_time(e[3]))
+        return nrec, mlen
+
+    for _ in range(args.warmup):
+        step(False)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        nrec, mlen = step(True)
+    t1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms = torch.tensor([t0.elapsed_time(t1) / args.steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    tot = torch.tensor([float(nrec), float(launches[0])], device=dev, dtype=torch.float64)
+    dist.all_reduce(tot)
+    ms_step = float(ms.item())
+    clk = clocks.stop() if rank == 0 else None
+    if rank == 0:
+        total_records = n * world
+        assert int(tot[0].item()) == total_records, "records lost in the shuffle"
+        value = total_records * REC / (ms_step * 1e-3) / 1e9
+        peak, peak_src = hbm_peak()
+        avg = {k: round(sum(v) / len(v), 3) for k, v in phase_ms.items()}
+        sent = int(n * OUT_REC * (world - 1) / world)
+        line = {"metric": "sorted KV GB/s (16B key / 64B val)", "value": round(value, 3), "unit": "GB/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": workload_config(world, n), "clocks": clk, "gpu_launches": int(tot[1].item()),
+                "e2e": None,
+                "phases_ms_rank0": avg,
+                "nvlink": {"bytes_sent_per_gpu_per_step": sent,
+                           "achieved_GBps_per_gpu": round(sent / (avg["exchange"] * 1e-3) / 1e9, 1) if avg["exchange"] else None,
+                           "reference_GBps": 770, "note": "variable-size all-to-all (NCCL send/recv) incl. index all-gather"},
+                "roofline": {"bound": "hbm", "achieved": round(n * (2 * 162) / (ms_step * 1e-3) / 1e9, 1), "peak": peak,
+                             "unit": "GB/s", "frac": round(n * (2 * 162) / (ms_step * 1e-3) / 1e9 / peak, 4),
+                             "traffic": None, "peak_source": peak_src,
+                             "note": "per GPU: sort (162 B/rec) + merge (164 B/rec) algorithmic bytes over the whole step"},
+                "cpu_baseline": None}
+        print(json.dumps(line))
+    dist.destroy_process_group()
+    return 0

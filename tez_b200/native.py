@@ -115,10 +115,13 @@ class GpuSorter:
 
 
 class GpuMerger:
-    def __init__(self, segments, comparator=CMP_BYTES, device=0, has_header=True, device_ptrs=False, fixed=None):
+    def __init__(self, segments, comparator=CMP_BYTES, device=0, has_header=True, device_ptrs=False, fixed=None,
+                 partitions=None, num_partitions=1, send_empty=True):
         """segments: list of bytes / uint8 arrays (host) or (ptr, len) tuples when device_ptrs."""
         self.L = _lib.load()
-        self.conf = make_conf(1, comparator=comparator, partitioner=PART_GIVEN, device=device, fixed=fixed)
+        self.conf = make_conf(num_partitions, comparator=comparator, partitioner=PART_GIVEN, device=device, fixed=fixed,
+                              send_empty=send_empty)
+        self.P = num_partitions
         self._keep = []
         arr = (Segment * max(1, len(segments)))()
         flags = (SEG_HAS_HEADER if has_header else 0) | (SEG_DEVICE if device_ptrs else 0)
@@ -131,6 +134,7 @@ class GpuMerger:
                 arr[i].data = a.ctypes.data if a.size else None
                 arr[i].len = a.size
             arr[i].flags = flags
+            arr[i].partition = 0 if partitions is None else int(partitions[i])
         self.h = C.c_void_p()
         check(self.L.tezgpu_merge_open(C.byref(self.conf), arr, len(segments), C.byref(self.h)))
 
@@ -188,6 +192,15 @@ class GpuMerger:
         check(self.L.tezgpu_merge_write_ifile_device(self.h, d_out, out_cap, 1 if rle else 0, C.byref(raw),
                                                      C.byref(part), C.byref(st)))
         return raw.value, part.value, st.as_dict()
+
+    def write_partitions_device(self, d_out, out_cap, rle=False):
+        """Batched reduce side: P merged segments back to back. Returns (out_len, index[P,3], stats)."""
+        n = C.c_uint64()
+        index = np.zeros((self.P, 3), dtype=np.int64)
+        st = Stats()
+        check(self.L.tezgpu_merge_write_partitions_device(self.h, d_out, out_cap, 1 if rle else 0, C.byref(n), _ptr(index),
+                                                          C.byref(st)))
+        return n.value, index, st.as_dict()
 
     def stream(self):
         return self.L.tezgpu_merge_stream(self.h)
