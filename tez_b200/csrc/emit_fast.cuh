@@ -139,6 +139,7 @@ __global__ void __launch_bounds__(FE_THREADS) k_emit_fast(FastEmitParams fp) {
   const uint32_t lane_pow = e.crc->pow_word[31 - lane];
   const uint32_t img_base = (uint32_t)__cvta_generic_to_shared(s_img);
   const uint8_t *__restrict__ kv = e.rec.kv;
+  const uint8_t *kv_end = kv + e.rec.kv_bytes;
   const uint32_t rec_size = e.rec_size, hdr_len = e.fixed_hdr_len, stride = fp.stride;
 
   for (uint32_t tile = blockIdx.x; tile < fp.ntiles; tile += gridDim.x) {
@@ -176,8 +177,8 @@ __global__ void __launch_bounds__(FE_THREADS) k_emit_fast(FastEmitParams fp) {
             const uint8_t *a = kv + s_off[j] + 16u * c;
             const uint32_t sh = (uint32_t)((uintptr_t)a & 15u);
             const uint4 *pa = reinterpret_cast<const uint4 *>(a - sh);
-            uint4 lo4 = __ldg(pa);
-            uint4 hi4 = sh ? __ldg(pa + 1) : lo4;
+            uint4 lo4 = load16_clamped(reinterpret_cast<const uint8_t *>(pa), kv, kv_end);
+            uint4 hi4 = sh ? load16_clamped(reinterpret_cast<const uint8_t *>(pa + 1), kv, kv_end) : lo4;
             const uint32_t bsh = (sh & 3u) * 8u;
             uint32_t w0, w1, w2, w3, w4;
             switch (sh >> 2) {

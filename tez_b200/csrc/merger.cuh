@@ -45,19 +45,29 @@ __global__ void __launch_bounds__(CRCV_THREADS)
   const uint64_t body_bytes = sd.body_end - sd.body0;
   const uint64_t a = (uint64_t)(piece - piece_start[lo]) * CRC_PIECE;
   const uint64_t b = min(body_bytes, a + CRC_PIECE);
-  const uint8_t *base = data + sd.off + sd.body0;  // 4-byte aligned (segments start 16-byte aligned, body0 in {0,4})
-  const uint32_t W = (uint32_t)((b - a) >> 2);
-  const uint32_t *w32 = reinterpret_cast<const uint32_t *>(base + a);
+  // piece = body bytes [a, b); word-aligned window [wlo, whi) around it: leading bytes of the first word that precede
+  // the piece are masked to zero (a remainder with zero initial value ignores leading zeros), trailing bytes are
+  // folded in bytewise by lane 0
+  const uint8_t *base = data + sd.off + sd.body0;
+  const uint8_t *pa = base + a, *pb = base + b;
+  const uint32_t mis = (uint32_t)((uintptr_t)pa & 3u);
+  const uint32_t *w32 = reinterpret_cast<const uint32_t *>(pa - mis);
+  const uint32_t W = (uint32_t)(((pb - (pa - mis))) >> 2);  // whole words starting at the aligned-down address
+  const uint32_t head_mask = 0xFFFFFFFFu << (8u * mis);
   __syncthreads();
   uint32_t c = 0;
   if (W + tid >= CRCV_THREADS && W > 0) {
     const uint32_t last_i = W - CRCV_THREADS + tid;
     uint32_t i = last_i % CRCV_THREADS;
     for (; i < last_i; i += CRCV_THREADS) {
-      uint32_t x = c ^ w32[i];
+      uint32_t w = w32[i];
+      if (i == 0) w &= head_mask;
+      uint32_t x = c ^ w;
       c = s_adv[x & 0xFF] ^ s_adv[256 + ((x >> 8) & 0xFF)] ^ s_adv[512 + ((x >> 16) & 0xFF)] ^ s_adv[768 + (x >> 24)];
     }
-    uint32_t x = c ^ w32[last_i];
+    uint32_t w = w32[last_i];
+    if (last_i == 0) w &= head_mask;
+    uint32_t x = c ^ w;
     c = s_tab[768 + (x & 0xFF)] ^ s_tab[512 + ((x >> 8) & 0xFF)] ^ s_tab[256 + ((x >> 16) & 0xFF)] ^ s_tab[x >> 24];
   }
   s_part[tid] = c;
@@ -74,7 +84,8 @@ __global__ void __launch_bounds__(CRCV_THREADS)
     for (int o = 16; o > 0; o >>= 1) q ^= __shfl_xor_sync(0xffffffffu, q, o);
     if (lane == 0) {
       uint32_t raw = q;
-      for (uint64_t x = a + 4ull * W; x < b; x++) raw = s_tab[(raw ^ base[x]) & 0xFF] ^ (raw >> 8);
+      const uint8_t *tail = (W > 0) ? (pa - mis) + 4ull * W : pa;  // W == 0: fewer than a word, all bytewise
+      for (const uint8_t *x = tail; x < pb; x++) raw = s_tab[(raw ^ *x) & 0xFF] ^ (raw >> 8);
       TileCrc tc;
       tc.raw = raw;
       tc.p = lo;
@@ -82,6 +93,18 @@ __global__ void __launch_bounds__(CRCV_THREADS)
       out[piece] = tc;
     }
   }
+}
+
+// verifyHeaderMagic + compressed flag (SORT/IFile.java:1004-1016): 1 = bad magic, 2 = compressed segment
+__global__ void k_check_headers(const uint8_t *__restrict__ data, const SegDesc *__restrict__ segs, uint32_t nseg,
+                                int *__restrict__ bad_magic, int *__restrict__ compressed) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nseg) return;
+  const SegDesc sd = segs[s];
+  if (!sd.has_header) return;
+  const uint8_t *h = data + sd.off;
+  if (!(h[0] == 'T' && h[1] == 'I' && h[2] == 'F')) atomicExch(bad_magic, (int)s + 1);
+  else if (h[3] != 0) atomicExch(compressed, (int)s + 1);
 }
 
 // compares the folded remainder with the big-endian trailer (SORT/IFileInputStream.java:235-289)
@@ -278,20 +301,31 @@ class Merger {
   }
   uint32_t fixed_klen = 0, fixed_vlen = 0;
   bool parsed_fixed = false;
+  uint32_t data_slack = 32;
 
   explicit Merger(const tezgpu_conf &c) : pipe(pipe_conf(c)), fixed_klen(c.fixed_key_len), fixed_vlen(c.fixed_val_len) {}
 
   void open(const tezgpu_segment *in, uint32_t nseg) {
     cudaStream_t st = pipe.stream;
     TG_CUDA(cudaSetDevice(pipe.conf.device));
-    // ---- stage all segments contiguously (16-byte aligned starts, 32 bytes of slack)
+    // ---- segments already on this device are used in place (no copy; kernels handle any byte alignment);
+    //      host segments are staged contiguously with 16-byte aligned starts
     segs.resize(nseg);
+    bool all_device = nseg > 0;
+    for (uint32_t s = 0; s < nseg; s++) all_device &= (in[s].flags & TEZGPU_SEG_DEVICE) != 0;
     uint64_t off = 0;
+    uintptr_t lo_addr = ~(uintptr_t)0, hi_addr = 0;
+    if (all_device)
+      for (uint32_t s = 0; s < nseg; s++) {
+        lo_addr = std::min(lo_addr, (uintptr_t)in[s].data);
+        hi_addr = std::max(hi_addr, (uintptr_t)in[s].data + in[s].len);
+      }
+    lo_addr &= ~(uintptr_t)15;
     for (uint32_t s = 0; s < nseg; s++) {
       TG_CHECK(in[s].data || in[s].len == 0, TEZGPU_E_INVALID, "null segment");
       const bool hdr = in[s].flags & TEZGPU_SEG_HAS_HEADER;
       TG_CHECK(in[s].len >= (hdr ? 10u : 6u), TEZGPU_E_FORMAT, "IFile segment shorter than an empty segment");
-      segs[s].off = off;
+      segs[s].off = all_device ? (uint64_t)((uintptr_t)in[s].data - lo_addr) : off;
       segs[s].len = in[s].len;
       segs[s].body0 = hdr ? 4 : 0;
       segs[s].body_end = in[s].len - 4;
@@ -300,27 +334,34 @@ class Merger {
       TG_CHECK((int)in[s].partition < pipe.conf.num_partitions, TEZGPU_E_INVALID, "segment partition out of range");
       off = align_up(off + in[s].len, 16);
     }
-    seg_bytes = off;
-    d_data.ensure(off + 64);
-    for (uint32_t s = 0; s < nseg; s++) {
-      if (!in[s].len) continue;
-      const bool dev = in[s].flags & TEZGPU_SEG_DEVICE;
-      TG_CUDA(cudaMemcpyAsync(d_data.as<uint8_t>() + segs[s].off, in[s].data, in[s].len,
-                              dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    if (all_device) {
+      data = reinterpret_cast<const uint8_t *>(lo_addr);
+      seg_bytes = (uint64_t)(hi_addr - lo_addr);
+      data_slack = 0;  // caller's buffer: never read past its end
+    } else {
+      seg_bytes = off;
+      d_data.ensure(off + 64);
+      for (uint32_t s = 0; s < nseg; s++) {
+        if (!in[s].len) continue;
+        const bool dev = in[s].flags & TEZGPU_SEG_DEVICE;
+        TG_CUDA(cudaMemcpyAsync(d_data.as<uint8_t>() + segs[s].off, in[s].data, in[s].len,
+                                dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+      }
+      data = d_data.as<uint8_t>();
+      data_slack = 32;
     }
-    data = d_data.as<uint8_t>();
     d_segs.ensure((size_t)(nseg ? nseg : 1) * sizeof(SegDesc));
     if (nseg) TG_CUDA(cudaMemcpyAsync(d_segs.p, segs.data(), (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
-    TG_CUDA(cudaStreamSynchronize(st));  // caller's buffers may go away after open()
-
-    // ---- header checks (verifyHeaderMagic / compressed flag, SORT/IFile.java:1004-1016) on the host copy of 4 bytes
-    for (uint32_t s = 0; s < nseg; s++) {
-      if (!segs[s].has_header) continue;
-      uint8_t h[4];
-      if (in[s].flags & TEZGPU_SEG_DEVICE) TG_CUDA(cudaMemcpy(h, in[s].data, 4, cudaMemcpyDeviceToHost));
-      else memcpy(h, in[s].data, 4);
-      TG_CHECK(h[0] == 'T' && h[1] == 'I' && h[2] == 'F', TEZGPU_E_FORMAT, "Not a valid ifile header");
-      TG_CHECK(h[3] == 0, TEZGPU_E_UNSUPPORTED, "compressed IFile segments are not supported on the device path");
+    TG_CUDA(cudaMemsetAsync(pipe.small.p, 0, 16384, st));
+    if (nseg) {
+      k_check_headers<<<(uint32_t)div_up(nseg, 128), 128, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, pipe.d_error(),
+                                                                 pipe.d_error() + 1);
+      launches++;
+      int flags2[2] = {0, 0};
+      TG_CUDA(cudaMemcpyAsync(flags2, pipe.d_error(), 8, cudaMemcpyDeviceToHost, st));
+      TG_CUDA(cudaStreamSynchronize(st));  // also: the caller's host buffers may go away after open()
+      TG_CHECK(flags2[0] == 0, TEZGPU_E_FORMAT, "Not a valid ifile header (segment " + std::to_string(flags2[0] - 1) + ")");
+      TG_CHECK(flags2[1] == 0, TEZGPU_E_UNSUPPORTED, "compressed IFile segments are not supported on the device path");
     }
 
     const CrcTables *d_crc = DeviceConstants::get(pipe.conf.device).d_crc;
@@ -421,7 +462,7 @@ class Merger {
     Records r;
     memset(&r, 0, sizeof(r));
     r.kv = data;
-    r.kv_bytes = align_up(seg_bytes, 16) + 32;
+    r.kv_bytes = data_slack ? align_up(seg_bytes, 16) + data_slack : seg_bytes;
     r.key_off = d_koff.as<uint64_t>();
     r.val_off = d_voff.as<uint64_t>();
     r.key_len = d_klen.as<uint32_t>();

@@ -523,6 +523,17 @@ struct EmitEntry {      // one record (or the header / EOF pseudo record) of a t
   uint8_t tail_fd;      // V_END_MARKER closing a run that ends the segment
 };
 
+// 16 aligned bytes at p; bytes outside [lo, hi) read as zero (never touches memory outside the buffer)
+__device__ __forceinline__ uint4 load16_clamped(const uint8_t *p, const uint8_t *__restrict__ lo, const uint8_t *__restrict__ hi) {
+  if (p >= lo && p + 16 <= hi) return *reinterpret_cast<const uint4 *>(p);
+  uint32_t w[4] = {0, 0, 0, 0};
+  for (int b = 0; b < 16; b++) {
+    const uint8_t *q = p + b;
+    if (q >= lo && q < hi) w[b >> 2] |= (uint32_t)(*q) << (8 * (b & 3));
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // merges `len` source bytes starting at global address src into bytes [o, o+len) of the 16-byte accumulator
 __device__ __forceinline__ void merge_bytes(uint32_t acc[4], const uint8_t *__restrict__ src, uint32_t o, uint32_t len,
                                             const uint8_t *__restrict__ lo, const uint8_t *__restrict__ hi) {
@@ -531,8 +542,8 @@ __device__ __forceinline__ void merge_bytes(uint32_t acc[4], const uint8_t *__re
   uint32_t sh = (uint32_t)((uintptr_t)first & 15u);
   const uint8_t *wb = first - sh;
   uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
-  if (sh + o < 16u && wb >= lo && wb + 16 <= hi) v0 = *reinterpret_cast<const uint4 *>(wb);
-  if (sh + o + len > 16u && wb + 16 >= lo && wb + 32 <= hi) v1 = *reinterpret_cast<const uint4 *>(wb + 16);
+  if (sh + o < 16u) v0 = load16_clamped(wb, lo, hi);
+  if (sh + o + len > 16u) v1 = load16_clamped(wb + 16, lo, hi);
   const uint32_t bsh = (sh & 3u) * 8u;
   uint32_t r0, r1, r2, r3;
   switch (sh >> 2) {

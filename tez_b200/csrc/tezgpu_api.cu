@@ -294,16 +294,13 @@ int32_t tezgpu_sorter_sort_device_fixed(tezgpu_sorter *h, const void *d_kv, cons
   Records r;
   memset(&r, 0, sizeof(r));
   r.kv = (const uint8_t *)d_kv;
-  r.kv_bytes = n * ((uint64_t)h->klen + h->vlen);  // no read past the caller's buffer
-  r.kv_bytes -= r.kv_bytes % 16;
-  if (r.kv_bytes < n * ((uint64_t)h->klen + h->vlen)) r.kv_bytes += 0;  // tail vector (if any) is read bytewise-safe below
+  r.kv_bytes = n * ((uint64_t)h->klen + h->vlen);  // exact: boundary loads are clamped, nothing is read past the caller's buffer
   r.partition = (const int32_t *)d_partition;
   r.n = (uint32_t)n;
   r.klen = h->klen;
   r.vlen = h->vlen;
   r.fixed = 1;
-  TG_CHECK((n * ((uint64_t)h->klen + h->vlen)) % 16 == 0 && ((uintptr_t)d_kv & 15u) == 0, TEZGPU_E_INVALID,
-           "device-resident input must be 16-byte aligned with a total size that is a multiple of 16");
+  TG_CHECK(((uintptr_t)d_kv & 15u) == 0, TEZGPU_E_INVALID, "device-resident input must be 16-byte aligned");
   tezgpu_stats st;
   h->pipe.run(r, (uint8_t *)d_out, out_cap, out_len, index, &st);
   st.output_bytes = (int64_t)(n * ((uint64_t)h->klen + h->vlen));
