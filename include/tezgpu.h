@@ -178,6 +178,10 @@ int32_t tezgpu_merge_write_ifile_device(tezgpu_merger *m, void *d_out, uint64_t 
  * names its partition; writes the P merged segments back to back like a file.out and fills index[3*P]. */
 int32_t tezgpu_merge_write_partitions_device(tezgpu_merger *m, void *d_out, uint64_t out_cap, int32_t rle,
                                              uint64_t *out_len, int64_t *index, tezgpu_stats *stats);
+/* same, written to file.out + file.out.index (mode 0640): the final merge of PipelinedSorter.flush over several spills
+ * (SORT/PipelinedSorter.java:774-836) */
+int32_t tezgpu_merge_write_partitions(tezgpu_merger *m, const char *out_path, const char *index_path, int32_t rle,
+                                      int64_t *index, tezgpu_stats *stats);
 void *tezgpu_merge_stream(tezgpu_merger *m);
 int32_t tezgpu_merge_close(tezgpu_merger *m);
 

@@ -59,8 +59,34 @@ SYMBOLS = [
     ("tezgpu_merge_output_bound", C.c_uint64, [_V]),
     ("tezgpu_merge_write_ifile_device", C.c_int32, [_V, _V, C.c_uint64, C.c_int32, _P(C.c_int64), _P(C.c_int64), _P(Stats)]),
     ("tezgpu_merge_write_partitions_device", C.c_int32, [_V, _V, C.c_uint64, C.c_int32, _P(C.c_uint64), _V, _P(Stats)]),
+    ("tezgpu_merge_write_partitions", C.c_int32, [_V, C.c_char_p, C.c_char_p, C.c_int32, _V, _P(Stats)]),
     ("tezgpu_merge_stream", _V, [_V]),
     ("tezgpu_merge_close", C.c_int32, [_V]),
+]
+
+RT_SYMBOLS = [
+    ("tezrt_last_error", C.c_char_p, []),
+    ("tezrt_output_create", C.c_int32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, _P(_V)]),
+    ("tezrt_output_initialize", C.c_int32, [_V, _P(C.c_int64)]),
+    ("tezrt_output_memory_assigned", C.c_int32, [_V, C.c_int64]),
+    ("tezrt_output_start", C.c_int32, [_V]),
+    ("tezrt_output_write", C.c_int32, [_V, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_int32]),
+    ("tezrt_output_close", C.c_int32, [_V, _P(C.c_int32)]),
+    ("tezrt_output_event", C.c_int32, [_V, C.c_int32, _P(C.c_int32), _P(_V), _P(C.c_uint64), _P(C.c_int32), _P(C.c_int32)]),
+    ("tezrt_output_counter", C.c_int64, [_V, C.c_char_p]),
+    ("tezrt_output_num_spills", C.c_int32, [_V]),
+    ("tezrt_output_file", C.c_char_p, [_V]),
+    ("tezrt_output_index_file", C.c_char_p, [_V]),
+    ("tezrt_output_destroy", C.c_int32, [_V]),
+    ("tezrt_input_create", C.c_int32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, _P(_V)]),
+    ("tezrt_input_initialize", C.c_int32, [_V, _P(C.c_int64)]),
+    ("tezrt_input_start", C.c_int32, [_V]),
+    ("tezrt_input_add_local_output", C.c_int32, [_V, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32]),
+    ("tezrt_input_wait_ready", C.c_int32, [_V]),
+    ("tezrt_input_next", C.c_int32, [_V, _P(_V), _P(C.c_uint32)]),
+    ("tezrt_input_next_value", C.c_int32, [_V, _P(_V), _P(C.c_uint32)]),
+    ("tezrt_input_counter", C.c_int64, [_V, C.c_char_p]),
+    ("tezrt_input_destroy", C.c_int32, [_V]),
 ]
 
 _lib = None
@@ -75,7 +101,7 @@ def load():
                 "tez_b200: %s is missing -- build it with `python -m tez_b200.build` "
                 "(the hot path has no Python or CPU fallback)" % LIB_PATH)
         L = C.CDLL(LIB_PATH)
-        for name, res, args in SYMBOLS:
+        for name, res, args in SYMBOLS + RT_SYMBOLS:
             fn = getattr(L, name)  # AttributeError if the ABI and the header drift apart
             fn.restype = res
             fn.argtypes = args
@@ -94,3 +120,8 @@ class TezGpuError(IOError):
 def check(rc):
     if rc != 0:
         raise TezGpuError(rc, load().tezgpu_last_error().decode("utf-8", "replace"))
+
+
+def check_rt(rc):
+    if rc != 0:
+        raise TezGpuError(rc, load().tezrt_last_error().decode("utf-8", "replace"))

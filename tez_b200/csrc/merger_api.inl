@@ -84,6 +84,31 @@ int32_t tezgpu_merge_write_partitions_device(tezgpu_merger *m, void *d_out, uint
   TG_API_END
 }
 
+int32_t tezgpu_merge_write_partitions(tezgpu_merger *m, const char *out_path, const char *index_path, int32_t rle,
+                                      int64_t *index, tezgpu_stats *stats) {
+  TG_API_BEGIN
+  TG_CHECK(m && out_path && index_path, TEZGPU_E_INVALID, "null argument");
+  Merger &mm = m->m;
+  const int P = mm.pipe.conf.num_partitions;
+  mm.d_out.ensure(mm.output_bound());
+  std::vector<int64_t> idx((size_t)P * 3, 0);
+  uint64_t len = 0;
+  tezgpu_stats st;
+  mm.write_partitions_device(mm.d_out.as<uint8_t>(), mm.d_out.cap, rle, &len, idx.data(), &st);
+  mm.h_out.ensure(len + 16);
+  if (len) {
+    TG_CUDA(cudaMemcpyAsync(mm.h_out.p, mm.d_out.p, len, cudaMemcpyDeviceToHost, mm.pipe.stream));
+    TG_CUDA(cudaStreamSynchronize(mm.pipe.stream));
+  }
+  write_file_0640(out_path, mm.h_out.p, len);
+  std::vector<uint8_t> b;
+  spill_record_bytes(idx.data(), P, b);
+  write_file_0640(index_path, b.data(), b.size());
+  if (index) memcpy(index, idx.data(), (size_t)P * 24);
+  if (stats) *stats = st;
+  TG_API_END
+}
+
 void *tezgpu_merge_stream(tezgpu_merger *m) { return m ? (void *)m->m.pipe.stream : nullptr; }
 
 int32_t tezgpu_merge_close(tezgpu_merger *m) {
