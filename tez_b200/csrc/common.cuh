@@ -114,4 +114,13 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t *p) {
+  uint64_t v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(uint64_t *p, uint64_t v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
 }  // namespace tezgpu

@@ -47,7 +47,7 @@ class SortPipeline {
   // workspace (grow-only, reused across flushes)
   DeviceBuffer keysA, keysB, valsA, valsB, same, blk, small, tile_state, sizes, rec_off;
   DeviceBuffer t_pos[2], t_gid[2], t_lidx[2], t_key64[2], t_val[2], t_state;
-  DeviceBuffer seg_start, tile_start, part_start, d_index, seg_crc, tile_desc, tile_crc;
+  DeviceBuffer seg_start, tile_start, part_start, d_index, seg_crc, tile_desc, tile_crc, tie_state;
   PinnedBuffer h_small;
 
   explicit SortPipeline(const tezgpu_conf &c) : conf(c) {
@@ -93,6 +93,8 @@ class SortPipeline {
   uint32_t *d_tile_counter() { return small.as<uint32_t>() + 2056; }
   int *d_error() { return reinterpret_cast<int *>(small.as<uint32_t>() + 2064); }
   uint32_t *d_large() { return small.as<uint32_t>() + 2065; }
+  uint32_t *d_m() { return small.as<uint32_t>() + 2072; }
+  uint32_t *d_ticket() { return small.as<uint32_t>() + 2073; }
   unsigned long long *d_dups() { return reinterpret_cast<unsigned long long *>(small.as<uint32_t>() + 2066); }
   uint64_t *d_totals() { return reinterpret_cast<uint64_t *>(small.as<uint32_t>() + 2068); }
 
@@ -103,7 +105,37 @@ class SortPipeline {
     uint32_t *order = nullptr;  // sorted position -> record index
     uint64_t dup_count = 0, tie_records = 0;
     int launches = 0;
+    bool have_bounds = false, spec_layout = false;  // partition bounds / fixed-width layout already on the device
+    uint64_t spec_file_bytes = 0, spec_tiles = 0;
   } state;
+
+  EmitParams make_emit_params(const Records &rec, const uint32_t *order, int rle, bool merge_mode, uint8_t *d_out) {
+    EmitParams e;
+    memset(&e, 0, sizeof(e));
+    e.rec = rec;
+    e.order = order;
+    e.same = same.as<uint8_t>();
+    e.part_start = part_start.as<uint32_t>();
+    e.seg_start = seg_start.as<uint64_t>();
+    e.tile_start = tile_start.as<uint32_t>();
+    e.out = d_out;
+    e.seg_crc = seg_crc.as<uint32_t>();
+    e.crc = DeviceConstants::get(conf.device).d_crc;
+    e.rle = rle;
+    e.send_empty = conf.send_empty_partition_details;
+    e.merge_mode = merge_mode ? 1 : 0;
+    e.P = conf.num_partitions;
+    return e;
+  }
+  static void set_fixed_layout(EmitParams &e, const Records &rec) {
+    int h = 0;
+    for (int b = 0; b < vint_size_u32(rec.klen); b++) e.fixed_hdr[h++] = vint_byte_u32(rec.klen, b);
+    for (int b = 0; b < vint_size_u32(rec.vlen); b++) e.fixed_hdr[h++] = vint_byte_u32(rec.vlen, b);
+    e.fixed_hdr_len = h;
+    e.rec_size = h + rec.klen + rec.vlen;
+    e.recs_per_tile = std::max<uint32_t>(1, std::min<uint32_t>(EMIT_MAX_RECS, (EMIT_IMG_BYTES - 32) / e.rec_size));
+    e.rec_off = nullptr;
+  }
 
   void run(Records rec, uint8_t *d_out, uint64_t out_cap, uint64_t *out_len, int64_t *index, tezgpu_stats *stats) {
     sort_phase(rec);
@@ -126,6 +158,7 @@ class SortPipeline {
     rec.pbits = pbits;
     TG_CHECK(rec.hash_partition || rec.partition || n == 0 || P == 1, TEZGPU_E_INVALID, "partition ids required (partitioner=GIVEN)");
     int launches = 0;
+    state.have_bounds = state.spec_layout = false;
     timer.reset();
     timer.mark(stream);
 
@@ -176,35 +209,50 @@ class SortPipeline {
       if (done & 1) { K = keysB.as<uint32_t>(); order = valsB.as<uint32_t>(); }
       timer.mark(stream);
 
-      // ---------------- ties: records whose sort words collide are ordered by the rest of the key
-      k_tie_count<<<nblk, SCAN_THREADS, 0, stream>>>(K, n, blk.as<uint64_t>());
-      k_scan_block_sums<<<1, 1024, 0, stream>>>(blk.as<uint64_t>(), nblk);
-      launches += 2;
+      // ---------------- ties: records whose sort words collide are ordered by the rest of the key.
+      // One look-back scan compacts them, one comparator kernel orders the (common) small groups; the partition
+      // bounds and -- for fixed-width records -- the segment layout are computed speculatively so that the whole
+      // common path needs a single host round trip (tie count, large groups, duplicates, error flag, layout totals).
+      t_pos[0].ensure(n4); t_gid[0].ensure(n4); t_lidx[0].ensure(n4);  // worst case: every record is tied
+      tie_state.ensure(((size_t)nblk + 1) * 8);
+      TG_CUDA(cudaMemsetAsync(tie_state.p, 0, ((size_t)nblk + 1) * 8, stream));
+      const uint32_t depth0 = (uint32_t)((32 - pbits) / 8);
+      k_tie_scan<<<nblk, SCAN_THREADS, 0, stream>>>(K, order, n, tie_state.as<uint64_t>(), d_ticket(), t_pos[0].as<uint32_t>(),
+                                                    t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>(), d_m());
+      k_tie_small<<<(uint32_t)std::min<uint64_t>(div_up(n, 256), (uint64_t)num_sms * 8), 256, 0, stream>>>(
+          rec, t_pos[0].as<uint32_t>(), t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>(), d_m(), depth0, order,
+          same.as<uint8_t>(), d_dups(), d_large());
+      k_part_bounds<<<(uint32_t)div_up((uint64_t)P + 1, 256), 256, 0, stream>>>(K, n, P, pbits, part_start.as<uint32_t>());
+      launches += 3;
+      state.have_bounds = true;
+      state.spec_layout = false;
+      if (rec.fixed) {
+        EmitParams e = make_emit_params(rec, order, 0, false, nullptr);
+        set_fixed_layout(e, rec);
+        k_layout<<<1, 1024, 0, stream>>>(e, seg_start.as<uint64_t>(), tile_start.as<uint32_t>(), d_index.as<int64_t>(), d_totals());
+        launches++;
+        state.spec_layout = true;
+      }
       TG_CUDA(cudaGetLastError());
-      uint64_t *hs = h_small.as<uint64_t>();
-      TG_CUDA(cudaMemcpyAsync(&hs[0], blk.as<uint64_t>() + nblk, 8, cudaMemcpyDeviceToHost, stream));
-      TG_CUDA(cudaMemcpyAsync(&hs[1], d_error(), 4, cudaMemcpyDeviceToHost, stream));
+      uint32_t *hw = h_small.as<uint32_t>();
+      TG_CUDA(cudaMemcpyAsync(hw, small.as<uint32_t>() + 2064, 40, cudaMemcpyDeviceToHost, stream));
+      if (state.spec_layout)
+        TG_CUDA(cudaMemcpyAsync(h_small.as<uint8_t>() + 4096, d_index.p, (size_t)P * 24, cudaMemcpyDeviceToHost, stream));
       TG_CUDA(cudaStreamSynchronize(stream));
-      TG_CHECK((uint32_t)hs[1] == 0, TEZGPU_E_INVALID, "Illegal partition (outside [0, numPartitions))");
-      uint32_t m = (uint32_t)hs[0];
+      // words: [0] error, [1] large groups, [2..3] duplicates, [4..7] layout totals, [8] tied records
+      TG_CHECK(hw[0] == 0, TEZGPU_E_INVALID, "Illegal partition (outside [0, numPartitions))");
+      uint32_t m = hw[8];
       tie_records = m;
-      if (m) {
-        for (int s = 0; s < 2; s++) { t_pos[s].ensure((size_t)m * 4); t_gid[s].ensure((size_t)m * 4); t_lidx[s].ensure((size_t)m * 4); }
-        k_tie_compact<<<nblk, SCAN_THREADS, 0, stream>>>(K, order, n, blk.as<uint64_t>(), t_pos[0].as<uint32_t>(),
-                                                         t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>());
-        launches++;
-        uint32_t depth = (uint32_t)((32 - pbits) / 8);
+      memcpy(&dup_count, hw + 2, 8);
+      memcpy(&state.spec_file_bytes, hw + 4, 8);
+      memcpy(&state.spec_tiles, hw + 6, 8);
+      uint64_t *hs = h_small.as<uint64_t>() + 16;
+      if (m && hw[1]) {
+        // some group is larger than TIE_SMALL_MAX: radix refinement rounds over all tied records
+        for (int s2 = 0; s2 < 2; s2++) { t_pos[s2].ensure((size_t)m * 4); t_gid[s2].ensure((size_t)m * 4); t_lidx[s2].ensure((size_t)m * 4); }
+        TG_CUDA(cudaMemsetAsync(d_dups(), 0, 8, stream));
+        uint32_t depth = depth0;
         int cur = 0;
-        // small groups (the common case) are ordered by one comparator kernel
-        k_tie_small<<<(uint32_t)div_up(m, 256), 256, 0, stream>>>(rec, t_pos[0].as<uint32_t>(), t_gid[0].as<uint32_t>(),
-                                                                 t_lidx[0].as<uint32_t>(), m, depth, order, same.as<uint8_t>(),
-                                                                 d_dups(), d_large());
-        launches++;
-        TG_CUDA(cudaGetLastError());
-        TG_CUDA(cudaMemcpyAsync(&hs[0], d_large(), 4, cudaMemcpyDeviceToHost, stream));
-        TG_CUDA(cudaStreamSynchronize(stream));
-        if ((uint32_t)hs[0] == 0) m = 0;  // every group was small: done
-        else TG_CUDA(cudaMemsetAsync(d_dups(), 0, 8, stream));
         while (m) {
           t_key64[0].ensure((size_t)m * 8); t_key64[1].ensure((size_t)m * 8); t_val[0].ensure((size_t)m * 4);
           const uint32_t mblk = (uint32_t)div_up(m, SCAN_TILE);
@@ -279,56 +327,48 @@ class SortPipeline {
     if (timer.n > (n ? 4 : 2)) timer.n = n ? 4 : 2;  // re-emit: drop the marks of a previous emit
 
     // ---------------- layout + emit
-    EmitParams e;
-    memset(&e, 0, sizeof(e));
-    e.rec = rec;
-    e.order = order;
-    e.same = same.as<uint8_t>();
-    e.part_start = part_start.as<uint32_t>();
-    e.seg_start = seg_start.as<uint64_t>();
-    e.tile_start = tile_start.as<uint32_t>();
-    e.out = d_out;
-    e.seg_crc = seg_crc.as<uint32_t>();
-    e.crc = d_crc;
-    e.rle = rle;
-    e.send_empty = conf.send_empty_partition_details;
-    e.merge_mode = merge_mode ? 1 : 0;
-    e.P = P;
-    k_part_bounds<<<(uint32_t)div_up((uint64_t)P + 1, 256), 256, 0, stream>>>(K, n, P, pbits, part_start.as<uint32_t>());
-    const bool fixed_emit = rec.fixed && (!rle || dup_count == 0);
-    uint64_t bound = output_bound(n, rec.fixed ? (uint64_t)n * (rec.klen + rec.vlen) : rec.kv_bytes, P);
-    if (fixed_emit) {
-      int h = 0;
-      for (int b = 0; b < vint_size_u32(rec.klen); b++) e.fixed_hdr[h++] = vint_byte_u32(rec.klen, b);
-      for (int b = 0; b < vint_size_u32(rec.vlen); b++) e.fixed_hdr[h++] = vint_byte_u32(rec.vlen, b);
-      e.fixed_hdr_len = h;
-      e.rec_size = h + rec.klen + rec.vlen;
-      e.recs_per_tile = std::max<uint32_t>(1, std::min<uint32_t>(EMIT_MAX_RECS, (EMIT_IMG_BYTES - 32) / e.rec_size));
-      e.rec_off = nullptr;
-    } else {
-      uint64_t avg = n ? (rec.fixed ? (uint64_t)(rec.klen + rec.vlen) : rec.kv_bytes / n) + 4 : 16;
-      e.recs_per_tile = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(EMIT_MAX_RECS, (EMIT_IMG_BYTES - 32) / avg));
-      sizes.ensure(n4);
-      rec_off.ensure(((size_t)n + 2) * 8);
-      if (n) {
-        k_emit_sizes<<<(uint32_t)div_up(n, 256), 256, 0, stream>>>(e, K, sizes.as<uint32_t>());
-        k_sum_u32_blocks<<<nblk, SCAN_THREADS, 0, stream>>>(sizes.as<uint32_t>(), n, blk.as<uint64_t>());
-        k_scan_block_sums<<<1, 1024, 0, stream>>>(blk.as<uint64_t>(), nblk);
-        k_scan_u32_apply<<<nblk, SCAN_THREADS, 0, stream>>>(sizes.as<uint32_t>(), n, blk.as<uint64_t>(), rec_off.as<uint64_t>());
-        launches += 4;
-        TG_CUDA(cudaGetLastError());
-      } else {
-        TG_CUDA(cudaMemsetAsync(rec_off.p, 0, 16, stream));
-      }
-      e.rec_off = rec_off.as<uint64_t>();
+    EmitParams e = make_emit_params(rec, order, rle, merge_mode, d_out);
+    if (!state.have_bounds) {
+      k_part_bounds<<<(uint32_t)div_up((uint64_t)P + 1, 256), 256, 0, stream>>>(K, n, P, pbits, part_start.as<uint32_t>());
+      launches++;
     }
-    k_layout<<<1, 1024, 0, stream>>>(e, seg_start.as<uint64_t>(), tile_start.as<uint32_t>(), d_index.as<int64_t>(), d_totals());
-    launches += 2;
-    TG_CUDA(cudaGetLastError());
+    // constant-size framing is only valid when no record is written as a repeat (merge mode flags repeats on its own)
+    const bool fixed_emit = rec.fixed && (dup_count == 0 || (!rle && !merge_mode));
+    uint64_t bound = output_bound(n, rec.fixed ? (uint64_t)n * (rec.klen + rec.vlen) : rec.kv_bytes, P);
     uint64_t *hs = h_small.as<uint64_t>();
-    TG_CUDA(cudaMemcpyAsync(&hs[0], d_totals(), 16, cudaMemcpyDeviceToHost, stream));
-    TG_CUDA(cudaMemcpyAsync(h_small.as<uint8_t>() + 4096, d_index.p, (size_t)P * 24, cudaMemcpyDeviceToHost, stream));
-    TG_CUDA(cudaStreamSynchronize(stream));
+    if (fixed_emit && state.spec_layout) {
+      // layout, totals and index triples were produced during the sort phase (same parameters): no round trip here
+      set_fixed_layout(e, rec);
+      hs[0] = state.spec_file_bytes;
+      hs[1] = state.spec_tiles;
+    } else {
+      if (fixed_emit) {
+        set_fixed_layout(e, rec);
+      } else {
+        uint64_t avg = n ? (rec.fixed ? (uint64_t)(rec.klen + rec.vlen) : rec.kv_bytes / n) + 4 : 16;
+        e.recs_per_tile = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(EMIT_MAX_RECS, (EMIT_IMG_BYTES - 32) / avg));
+        sizes.ensure(n4);
+        rec_off.ensure(((size_t)n + 2) * 8);
+        if (n) {
+          k_emit_sizes<<<(uint32_t)div_up(n, 256), 256, 0, stream>>>(e, K, sizes.as<uint32_t>());
+          k_sum_u32_blocks<<<nblk, SCAN_THREADS, 0, stream>>>(sizes.as<uint32_t>(), n, blk.as<uint64_t>());
+          k_scan_block_sums<<<1, 1024, 0, stream>>>(blk.as<uint64_t>(), nblk);
+          k_scan_u32_apply<<<nblk, SCAN_THREADS, 0, stream>>>(sizes.as<uint32_t>(), n, blk.as<uint64_t>(), rec_off.as<uint64_t>());
+          launches += 4;
+          TG_CUDA(cudaGetLastError());
+        } else {
+          TG_CUDA(cudaMemsetAsync(rec_off.p, 0, 16, stream));
+        }
+        e.rec_off = rec_off.as<uint64_t>();
+      }
+      k_layout<<<1, 1024, 0, stream>>>(e, seg_start.as<uint64_t>(), tile_start.as<uint32_t>(), d_index.as<int64_t>(), d_totals());
+      launches++;
+      TG_CUDA(cudaGetLastError());
+      TG_CUDA(cudaMemcpyAsync(&hs[0], d_totals(), 16, cudaMemcpyDeviceToHost, stream));
+      TG_CUDA(cudaMemcpyAsync(h_small.as<uint8_t>() + 4096, d_index.p, (size_t)P * 24, cudaMemcpyDeviceToHost, stream));
+      TG_CUDA(cudaStreamSynchronize(stream));
+      state.spec_layout = false;  // the device layout now belongs to this emit
+    }
     const uint64_t file_bytes = hs[0];
     const uint64_t tiles = hs[1];
     TG_CHECK(file_bytes <= bound, TEZGPU_E_INVALID, "internal: output exceeds bound");

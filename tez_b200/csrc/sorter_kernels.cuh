@@ -119,8 +119,9 @@ struct TileFlags {
   bool t[SCAN_IPT], h[SCAN_IPT];
 };
 
-__device__ __forceinline__ void tile_load_flags(const uint32_t *__restrict__ K, uint32_t n, uint32_t *s_k, TileFlags &f) {
-  const uint32_t base = blockIdx.x * SCAN_TILE;
+__device__ __forceinline__ void tile_load_flags(const uint32_t *__restrict__ K, uint32_t n, uint32_t *s_k, TileFlags &f,
+                                                uint32_t tile) {
+  const uint32_t base = tile * SCAN_TILE;
   for (uint32_t i = threadIdx.x; i < SCAN_TILE + 2; i += SCAN_THREADS) {
     int64_t gi = (int64_t)base + i - 1;
     s_k[i] = (gi >= 0 && gi < (int64_t)n) ? K[gi] : 0u;
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_tie_count(const uint32_t *__re
   __shared__ uint32_t s_k[SCAN_TILE + 2];
   __shared__ uint64_t s_warp[SCAN_THREADS / 32];
   TileFlags f;
-  tile_load_flags(K, n, s_k, f);
+  tile_load_flags(K, n, s_k, f, blockIdx.x);
   uint64_t s = 0;
 #pragma unroll
   for (int k = 0; k < SCAN_IPT; k++) s += (uint64_t)f.t[k] | ((uint64_t)f.h[k] << 32);
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
   __shared__ uint32_t s_k[SCAN_TILE + 2];
   __shared__ uint32_t s_ct[SCAN_IPT][SCAN_THREADS / 32], s_ch[SCAN_IPT][SCAN_THREADS / 32];
   TileFlags f;
-  tile_load_flags(K, n, s_k, f);
+  tile_load_flags(K, n, s_k, f, blockIdx.x);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt = lanemask_lt();
   uint32_t bt[SCAN_IPT], bh[SCAN_IPT];
@@ -197,6 +198,82 @@ __global__ void __launch_bounds__(SCAN_THREADS)
   }
 }
 
+// Single-pass version of k_tie_count + scan + k_tie_compact: chained scan with decoupled look-back over the tiles
+// (state = flag:2 | heads:31 | tied:31), so the sort words are read once and no host round trip is needed.
+// *m_out receives the number of tied records.
+constexpr uint64_t TIE_FLAG_AGG = 1ull << 62, TIE_FLAG_INCL = 2ull << 62, TIE_VAL_MASK = (1ull << 62) - 1;
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+    k_tie_scan(const uint32_t *__restrict__ K, const uint32_t *__restrict__ order, uint32_t n, uint64_t *state,
+               uint32_t *ticket, uint32_t *__restrict__ pos, uint32_t *__restrict__ gid, uint32_t *__restrict__ lidx,
+               uint32_t *__restrict__ m_out) {
+  __shared__ uint32_t s_k[SCAN_TILE + 2];
+  __shared__ uint32_t s_ct[SCAN_IPT][SCAN_THREADS / 32], s_ch[SCAN_IPT][SCAN_THREADS / 32];
+  __shared__ uint32_t s_tile;
+  __shared__ uint64_t s_base;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = s_tile;
+  TileFlags f;
+  tile_load_flags(K, n, s_k, f, tile);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = lanemask_lt();
+  uint32_t bt[SCAN_IPT], bh[SCAN_IPT];
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; k++) {
+    bt[k] = __ballot_sync(0xffffffffu, f.t[k]);
+    bh[k] = __ballot_sync(0xffffffffu, f.h[k]);
+    if (lane == 0) { s_ct[k][warp] = __popc(bt[k]); s_ch[k][warp] = __popc(bh[k]); }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t agg_t = 0, agg_h = 0;
+    for (int k = 0; k < SCAN_IPT; k++)
+      for (int w = 0; w < SCAN_THREADS / 32; w++) { agg_t += s_ct[k][w]; agg_h += s_ch[k][w]; }
+    const uint64_t agg = agg_t | (agg_h << 31);
+    uint64_t excl = 0;
+    if (tile == 0) {
+      st_volatile_u64(&state[0], TIE_FLAG_INCL | agg);
+    } else {
+      st_volatile_u64(&state[tile], TIE_FLAG_AGG | agg);
+      int64_t t = (int64_t)tile - 1;
+      while (true) {
+        uint64_t s = ld_volatile_u64(&state[t]);
+        uint64_t flag = s & ~TIE_VAL_MASK;
+        if (flag == 0) continue;
+        excl += s & TIE_VAL_MASK;
+        if (flag == TIE_FLAG_INCL) break;
+        t--;
+      }
+      st_volatile_u64(&state[tile], TIE_FLAG_INCL | (excl + agg));
+    }
+    s_base = excl;
+    if ((uint64_t)(tile + 1) * SCAN_TILE >= n) *m_out = (uint32_t)((excl + agg) & 0x7FFFFFFFull);
+  }
+  __syncthreads();
+  const uint64_t b0 = s_base;
+  uint32_t run_t = (uint32_t)(b0 & 0x7FFFFFFFull), run_h = (uint32_t)(b0 >> 31);
+  const uint32_t base = tile * SCAN_TILE;
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; k++) {
+    uint32_t pre_t = run_t, pre_h = run_h;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) {
+      uint32_t ct = s_ct[k][w], ch = s_ch[k][w];
+      if (w < warp) { pre_t += ct; pre_h += ch; }
+      run_t += ct; run_h += ch;
+    }
+    if (f.t[k]) {
+      uint32_t at = pre_t + __popc(bt[k] & lt);
+      uint32_t heads = pre_h + __popc(bh[k] & lt) + (f.h[k] ? 1u : 0u);
+      uint32_t i = base + k * SCAN_THREADS + threadIdx.x;
+      pos[at] = i;
+      gid[at] = heads - 1;
+      lidx[at] = order[i];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ small tie groups
 // full RawComparator order of two records' keys from normalised content byte `depth` on (bytes before it are equal)
 __device__ __forceinline__ int compare_keys_from(const Records &r, uint32_t ra, uint32_t rb, uint32_t depth) {
@@ -220,13 +297,10 @@ constexpr uint32_t TIE_SMALL_MAX = 16;
 // One thread per tied record: groups of at most TIE_SMALL_MAX records are ordered directly with the full comparator
 // (rank = #smaller + #equal-and-earlier).  With uniformly distributed keys almost every group has 2-3 members.
 // Larger groups are only counted; the host then runs the radix refinement rounds.
-__global__ void __launch_bounds__(256)
-    k_tie_small(Records r, const uint32_t *__restrict__ pos, const uint32_t *__restrict__ gid,
-                const uint32_t *__restrict__ lidx, uint32_t m, uint32_t depth, uint32_t *__restrict__ order,
-                uint8_t *__restrict__ same, unsigned long long *__restrict__ dup_count,
-                uint32_t *__restrict__ large_groups) {
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= m) return;
+__device__ __forceinline__ void tie_small_one(const Records &r, const uint32_t *__restrict__ pos, const uint32_t *__restrict__ gid,
+                                              const uint32_t *__restrict__ lidx, uint32_t m, uint32_t j, uint32_t depth,
+                                              uint32_t *__restrict__ order, uint8_t *__restrict__ same,
+                                              unsigned long long *__restrict__ dup_count, uint32_t *__restrict__ large_groups) {
   const uint32_t g = gid[j];
   uint32_t s = j;
   while (s > 0 && gid[s - 1] == g && j - s < TIE_SMALL_MAX) s--;
@@ -254,6 +328,16 @@ __global__ void __launch_bounds__(256)
     same[p] = 1;  // byte-identical to the key at sorted position p-1
     atomicAdd(dup_count, 1ull);
   }
+}
+
+__global__ void __launch_bounds__(256)
+    k_tie_small(Records r, const uint32_t *__restrict__ pos, const uint32_t *__restrict__ gid,
+                const uint32_t *__restrict__ lidx, const uint32_t *__restrict__ m_ptr, uint32_t depth,
+                uint32_t *__restrict__ order, uint8_t *__restrict__ same, unsigned long long *__restrict__ dup_count,
+                uint32_t *__restrict__ large_groups) {
+  const uint32_t m = *m_ptr;
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x)
+    tie_small_one(r, pos, gid, lidx, m, j, depth, order, same, dup_count, large_groups);
 }
 
 // ------------------------------------------------------------------------------------------------ refinement rounds
