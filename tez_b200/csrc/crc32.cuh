@@ -28,6 +28,8 @@ struct CrcTables {
   uint32_t slice[4][256];   // slice-by-4 byte tables: slice[k][b] = (b * x^(8*(k+1))) mod P, k = 0 is the classic table
   uint32_t adv[4][256];     // multiply-by-x^(32*EMIT_CRC_STRIDE_WORDS) byte tables (interleaved per-thread streams)
   uint32_t adv32[4][256];   // multiply-by-x^(32*32) byte tables (second-level fold of the per-thread partials)
+  uint32_t advc[4][256];    // multiply-by-x^(32*(4*stride-3)): 16-byte-chunk interleave (fused CRC + write-out)
+  uint32_t adv128[4][256];  // multiply-by-x^(32*128): second-level fold of chunk-interleaved partials
   uint32_t pow_word[512];   // x^(32*j), j < 512
   uint32_t pow0[4096];      // x^(8*a)
   uint32_t pow1[4096];      // x^(8*4096*a)
@@ -61,6 +63,12 @@ static inline void crc_build_tables(CrcTables &t, int stride_words) {
   uint32_t x32w = crc_host_xpow8((uint64_t)4 * 32);
   for (int k = 0; k < 4; k++)
     for (uint32_t b = 0; b < 256; b++) t.adv32[k][b] = crc_multmodp(b << (8 * k), x32w);
+  uint32_t xc = crc_host_xpow8((uint64_t)4 * (uint64_t)(4 * stride_words - 3)), x128 = crc_host_xpow8((uint64_t)4 * 128);
+  for (int k = 0; k < 4; k++)
+    for (uint32_t b = 0; b < 256; b++) {
+      t.advc[k][b] = crc_multmodp(b << (8 * k), xc);
+      t.adv128[k][b] = crc_multmodp(b << (8 * k), x128);
+    }
   for (int j = 0; j < 512; j++) t.pow_word[j] = crc_host_xpow8((uint64_t)4 * (uint64_t)j);
   uint32_t s0 = crc_host_xpow8(1), s1 = crc_host_xpow8(4096), s2 = crc_host_xpow8(1ull << 24);
   t.pow0[0] = t.pow1[0] = t.pow2[0] = 0x80000000u;

@@ -124,19 +124,19 @@ __global__ void __launch_bounds__(FE_THREADS) k_emit_fast(FastEmitParams fp) {
   __shared__ uint32_t s_idx[FE_MAX_RECS];
   __shared__ uint64_t s_off[ALIGNED ? 1 : FE_MAX_RECS];  // source offsets of the tile's records (explicit-offset mode)
   __shared__ uint32_t s_tab[4 * 256];    // slice-by-4 tables
-  __shared__ uint32_t s_adv[4 * 256];    // * x^(32*FE_THREADS)
-  __shared__ uint32_t s_adv32[4 * 256];  // * x^(32*32)
+  __shared__ uint32_t s_adv[4 * 256];    // * x^(32*(4*FE_THREADS-3)): skip to this thread's next 16-byte chunk
+  __shared__ uint32_t s_adv32[4 * 256];  // * x^(32*128): second-level fold
   __shared__ uint32_t s_part[FE_THREADS];
 
   const EmitParams &e = fp.e;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < 4 * 256; i += FE_THREADS) {
     s_tab[i] = (&e.crc->slice[0][0])[i];
-    s_adv[i] = (&e.crc->adv[0][0])[i];
-    s_adv32[i] = (&e.crc->adv32[0][0])[i];
+    s_adv[i] = (&e.crc->advc[0][0])[i];
+    s_adv32[i] = (&e.crc->adv128[0][0])[i];
   }
   // constant alignment multipliers: x^(32*(31-lane)) for the final in-warp fold
-  const uint32_t lane_pow = e.crc->pow_word[31 - lane];
+  const uint32_t lane_pow = e.crc->pow_word[4 * (31 - lane)];
   const uint32_t img_base = (uint32_t)__cvta_generic_to_shared(s_img);
   const uint8_t *__restrict__ kv = e.rec.kv;
   const uint8_t *kv_end = kv + e.rec.kv_bytes;
@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(FE_THREADS) k_emit_fast(FastEmitParams fp) {
 
     // ---- gather: lane <-> (record j, 16-byte piece c); all loads of a thread are issued before its stores
     const uint32_t npieces = nr * fp.cpr;
+    const uint32_t half_up = (nr + 1) >> 1;
     for (uint32_t q0 = tid; q0 < npieces; q0 += FE_THREADS * UNROLL) {
       uint4 v[UNROLL];
       uint32_t dst[UNROLL];
@@ -167,8 +168,11 @@ __global__ void __launch_bounds__(FE_THREADS) k_emit_fast(FastEmitParams fp) {
       for (int u = 0; u < UNROLL; u++) {
         uint32_t q = q0 + u * FE_THREADS;
         if (q < npieces) {
-          uint32_t j = fp.cpr == 1 ? q : __umulhi(q, fp.cpr_magic);
-          uint32_t c = q - j * fp.cpr;
+          uint32_t jp = fp.cpr == 1 ? q : __umulhi(q, fp.cpr_magic);
+          uint32_t c = q - jp * fp.cpr;
+          // even records first, then odd ones: the destination alignment (mod 4) alternates with the record parity
+          // when the emitted record size is 2 mod 4, so this keeps a warp on one store path
+          uint32_t j = jp < half_up ? 2u * jp : 2u * (jp - half_up) + 1u;
           if (ALIGNED) {
             v[u] = ldg_stream_v4(kv + (uint64_t)s_idx[j] * stride + 16u * c);
           } else {
@@ -210,52 +214,58 @@ __global__ void __launch_bounds__(FE_THREADS) k_emit_fast(FastEmitParams fp) {
     }
     __syncthreads();
 
-    // ---- CRC of the body bytes [cb0, cb1) of the image.  Leading zero bytes do not change a remainder with zero
-    // initial value, so the (possibly partial) first word is simply masked; trailing bytes are folded in at the end.
+    // ---- fused CRC + write-out.  Every thread streams its 16-byte chunks of the image to HBM and folds the same
+    // registers into the checksum: thread t owns the chunks whose distance from the end of the body is == T-1-t
+    // (mod T), so its partial always needs the constant alignment multiplier x^(128*(T-1-t)).  Leading bytes of the
+    // first chunk that precede the body are masked to zero (no effect on a remainder with zero initial value); the
+    // trailing partial chunk is folded bytewise by lane 0.
     const uint32_t cb0 = rec0, cb1 = body_end;
-    const uint32_t wa = cb0 >> 2, wb = cb1 >> 2;  // words [wa, wb): first one masked below
-    const uint32_t *img32 = reinterpret_cast<const uint32_t *>(s_img);
+    const uint32_t ca = cb0 >> 4, cz = cb1 >> 4;  // whole chunks [ca, cz) belong to the body (first one masked)
     {
-      // level 1: thread t owns the words whose distance from the end is == T-1-t (mod T): its partial always needs
-      // the same alignment multiplier x^(32*(T-1-t)), whatever the word count
+      uint8_t *dstg = e.out + (abs0 - lead);
       uint32_t c = 0;
-      if (wb > wa) {
-        const uint32_t W = wb - wa;
-        const uint32_t head_mask = 0xFFFFFFFFu << (8u * (cb0 & 3u));
-        if (W + tid >= FE_THREADS) {
-          const uint32_t last_i = W - FE_THREADS + tid;
-          uint32_t i = last_i % FE_THREADS;
-          for (; i < last_i; i += FE_THREADS) {
-            uint32_t w = img32[wa + i];
-            if (i == 0) w &= head_mask;
-            uint32_t x = c ^ w;
-            c = s_adv[x & 0xFF] ^ s_adv[256 + ((x >> 8) & 0xFF)] ^ s_adv[512 + ((x >> 16) & 0xFF)] ^ s_adv[768 + (x >> 24)];
+      if (cz > ca) {
+        const uint32_t Cn = cz - ca;
+        if (Cn + tid >= FE_THREADS) {
+          const uint32_t last_i = Cn - FE_THREADS + tid;
+          for (uint32_t i = last_i % FE_THREADS; i <= last_i; i += FE_THREADS) {
+            const uint32_t b0 = 16u * (ca + i);
+            uint4 v = *reinterpret_cast<const uint4 *>(s_img + b0);
+            if (b0 >= lead) stg_stream_v4(dstg + b0, v);
+            else for (uint32_t x = lead; x < b0 + 16u; x++) dstg[x] = s_img[x];  // ragged first chunk of the tile
+            if (i == 0 && (cb0 & 15u)) {  // zero the bytes before the body (segment header / previous tile's bytes)
+              const uint32_t skip = cb0 & 15u;
+              uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (uint32_t k = 0; k < 4; k++) {
+                if (skip >= 4 * k + 4) w[k] = 0;
+                else if (skip > 4 * k) w[k] &= 0xFFFFFFFFu << (8u * (skip - 4 * k));
+              }
+              v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            uint32_t x = c ^ v.x;
+            x = s_tab[768 + (x & 0xFF)] ^ s_tab[512 + ((x >> 8) & 0xFF)] ^ s_tab[256 + ((x >> 16) & 0xFF)] ^ s_tab[x >> 24];
+            x ^= v.y;
+            x = s_tab[768 + (x & 0xFF)] ^ s_tab[512 + ((x >> 8) & 0xFF)] ^ s_tab[256 + ((x >> 16) & 0xFF)] ^ s_tab[x >> 24];
+            x ^= v.z;
+            x = s_tab[768 + (x & 0xFF)] ^ s_tab[512 + ((x >> 8) & 0xFF)] ^ s_tab[256 + ((x >> 16) & 0xFF)] ^ s_tab[x >> 24];
+            x ^= v.w;
+            if (i == last_i) c = s_tab[768 + (x & 0xFF)] ^ s_tab[512 + ((x >> 8) & 0xFF)] ^ s_tab[256 + ((x >> 16) & 0xFF)] ^ s_tab[x >> 24];
+            else c = s_adv[x & 0xFF] ^ s_adv[256 + ((x >> 8) & 0xFF)] ^ s_adv[512 + ((x >> 16) & 0xFF)] ^ s_adv[768 + (x >> 24)];
           }
-          uint32_t w = img32[wa + last_i];
-          if (last_i == 0) w &= head_mask;
-          uint32_t x = c ^ w;
-          c = s_tab[768 + (x & 0xFF)] ^ s_tab[512 + ((x >> 8) & 0xFF)] ^ s_tab[256 + ((x >> 16) & 0xFF)] ^ s_tab[x >> 24];
         }
       }
       s_part[tid] = c;
+      // chunks outside [ca, cz): the tile's leading header-only chunk (cannot happen: header and body share chunk ca
+      // or follow it) and the trailing partial chunk
+      if (tid == 0) {
+        for (uint32_t x = max(lead, 16u * cz); x < body_end; x++) dstg[x] = s_img[x];
+        if (ca > (lead >> 4)) for (uint32_t x = lead; x < 16u * ca; x++) dstg[x] = s_img[x];
+      }
     }
     __syncthreads();
-
-    // ---- warps 1..7 stream the image out while warp 0 finishes the checksum
-    if (warp != 0) {
-      uint8_t *dstg = e.out + (abs0 - lead);
-      const uint32_t nchunks = (body_end + 15u) >> 4;
-      for (uint32_t cidx = tid - 32; cidx < nchunks; cidx += FE_THREADS - 32) {
-        uint32_t b0 = 16u * cidx, b1 = b0 + 16u;
-        if (b0 >= lead && b1 <= body_end) {
-          stg_stream_v4(dstg + b0, *reinterpret_cast<const uint4 *>(s_img + b0));
-        } else {
-          uint32_t a = max(b0, lead), b = min(b1, body_end);
-          for (uint32_t x = a; x < b; x++) dstg[x] = s_img[x];
-        }
-      }
-    } else {
-      // level 2: lane l folds partials l, l+32, ... (Horner with x^(32*32)), level 3: align by x^(32*(31-l)), xor-reduce
+    if (warp == 0) {
+      // level 2: lane l folds partials l, l+32, ... (Horner with x^(128*32)), level 3: align by x^(128*(31-l)), xor-reduce
       uint32_t q = 0;
 #pragma unroll
       for (int k = 0; k < FE_THREADS / 32; k++) {
@@ -267,11 +277,11 @@ __global__ void __launch_bounds__(FE_THREADS) k_emit_fast(FastEmitParams fp) {
       for (int o = 16; o > 0; o >>= 1) q ^= __shfl_xor_sync(0xffffffffu, q, o);
       if (lane == 0) {
         uint32_t raw = q;
-        if (wb <= wa) {  // fewer than 4 body bytes: bytewise from cb0
+        if (cz <= ca) {  // body shorter than one chunk: bytewise from cb0
           raw = 0;
           for (uint32_t b = cb0; b < cb1; b++) raw = s_tab[(raw ^ s_img[b]) & 0xFF] ^ (raw >> 8);
         } else {
-          for (uint32_t b = 4 * wb; b < cb1; b++) raw = s_tab[(raw ^ s_img[b]) & 0xFF] ^ (raw >> 8);
+          for (uint32_t b = 16u * cz; b < cb1; b++) raw = s_tab[(raw ^ s_img[b]) & 0xFF] ^ (raw >> 8);
         }
         TileCrc tc;
         tc.raw = raw;
