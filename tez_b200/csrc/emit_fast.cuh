@@ -57,9 +57,22 @@ __global__ void k_build_tiles(EmitParams e, TileDesc *__restrict__ tiles) {
 __global__ void k_crc_combine(const TileCrc *__restrict__ tc, uint32_t ntiles, const CrcTables *__restrict__ t,
                               uint32_t *__restrict__ seg_crc) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ntiles) return;
-  TileCrc c = tc[i];
-  if (c.raw) atomicXor(&seg_crc[c.p], crc_shift_bytes(t, c.raw, c.after));
+  const int lane = threadIdx.x & 31;
+  uint32_t p = 0xFFFFFFFFu, val = 0;
+  if (i < ntiles) {
+    TileCrc c = tc[i];
+    p = c.p;
+    val = c.raw ? crc_shift_bytes(t, c.raw, c.after) : 0u;
+  }
+  // tiles are ordered by segment: xor-reduce the runs of equal p inside the warp, one atomic per run
+  // (same-address atomics serialise at ~20 ns each)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t v2 = __shfl_up_sync(0xffffffffu, val, o), p2 = __shfl_up_sync(0xffffffffu, p, o);
+    if (lane >= o && p2 == p) val ^= v2;
+  }
+  uint32_t pn = __shfl_down_sync(0xffffffffu, p, 1);
+  if (p != 0xFFFFFFFFu && (lane == 31 || pn != p) && val) atomicXor(&seg_crc[p], val);
 }
 
 __device__ __forceinline__ void sts_b8(uint32_t a, uint32_t v) { asm volatile("st.shared.b8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }

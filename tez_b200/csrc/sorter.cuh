@@ -217,10 +217,21 @@ class SortPipeline {
       tie_state.ensure(((size_t)nblk + 1) * 8);
       TG_CUDA(cudaMemsetAsync(tie_state.p, 0, ((size_t)nblk + 1) * 8, stream));
       const uint32_t depth0 = (uint32_t)((32 - pbits) / 8);
+#ifdef TEZGPU_TIE_LOOKBACK
       k_tie_scan<<<nblk, SCAN_THREADS, 0, stream>>>(K, order, n, tie_state.as<uint64_t>(), d_ticket(), t_pos[0].as<uint32_t>(),
                                                     t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>(), d_m());
+      const uint32_t *d_m_ptr = d_m();
+#else
+      // count -> single-block scan of the per-tile counts -> compact; the tied-record count stays on the device
+      k_tie_count<<<nblk, SCAN_THREADS, 0, stream>>>(K, n, blk.as<uint64_t>());
+      k_scan_block_sums<<<1, 1024, 0, stream>>>(blk.as<uint64_t>(), nblk);
+      k_tie_compact<<<nblk, SCAN_THREADS, 0, stream>>>(K, order, n, blk.as<uint64_t>(), t_pos[0].as<uint32_t>(),
+                                                       t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>());
+      launches += 2;
+      const uint32_t *d_m_ptr = reinterpret_cast<const uint32_t *>(blk.as<uint64_t>() + nblk);  // low word = tied records
+#endif
       k_tie_small<<<(uint32_t)std::min<uint64_t>(div_up(n, 256), (uint64_t)num_sms * 8), 256, 0, stream>>>(
-          rec, t_pos[0].as<uint32_t>(), t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>(), d_m(), depth0, order,
+          rec, t_pos[0].as<uint32_t>(), t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>(), d_m_ptr, depth0, order,
           same.as<uint8_t>(), d_dups(), d_large());
       k_part_bounds<<<(uint32_t)div_up((uint64_t)P + 1, 256), 256, 0, stream>>>(K, n, P, pbits, part_start.as<uint32_t>());
       launches += 3;
@@ -235,7 +246,8 @@ class SortPipeline {
       }
       TG_CUDA(cudaGetLastError());
       uint32_t *hw = h_small.as<uint32_t>();
-      TG_CUDA(cudaMemcpyAsync(hw, small.as<uint32_t>() + 2064, 40, cudaMemcpyDeviceToHost, stream));
+      TG_CUDA(cudaMemcpyAsync(hw, small.as<uint32_t>() + 2064, 32, cudaMemcpyDeviceToHost, stream));
+      TG_CUDA(cudaMemcpyAsync(hw + 8, d_m_ptr, 4, cudaMemcpyDeviceToHost, stream));
       if (state.spec_layout)
         TG_CUDA(cudaMemcpyAsync(h_small.as<uint8_t>() + 4096, d_index.p, (size_t)P * 24, cudaMemcpyDeviceToHost, stream));
       TG_CUDA(cudaStreamSynchronize(stream));

@@ -211,9 +211,14 @@ __global__ void __launch_bounds__(SCAN_THREADS)
   __shared__ uint32_t s_ct[SCAN_IPT][SCAN_THREADS / 32], s_ch[SCAN_IPT][SCAN_THREADS / 32];
   __shared__ uint32_t s_tile;
   __shared__ uint64_t s_base;
+#ifdef TEZGPU_TICKET_ATOMIC
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
   __syncthreads();
   const uint32_t tile = s_tile;
+#else
+  (void)ticket; (void)s_tile;
+  const uint32_t tile = blockIdx.x;  // in-order dispatch of a 1-D grid (see radix_sort.cuh)
+#endif
   TileFlags f;
   tile_load_flags(K, n, s_k, f, tile);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -226,29 +231,43 @@ __global__ void __launch_bounds__(SCAN_THREADS)
     if (lane == 0) { s_ct[k][warp] = __popc(bt[k]); s_ch[k][warp] = __popc(bh[k]); }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    uint64_t agg_t = 0, agg_h = 0;
-    for (int k = 0; k < SCAN_IPT; k++)
-      for (int w = 0; w < SCAN_THREADS / 32; w++) { agg_t += s_ct[k][w]; agg_h += s_ch[k][w]; }
-    const uint64_t agg = agg_t | (agg_h << 31);
+  if (warp == 0) {
+    // block aggregate, then a warp-wide decoupled look-back: lane l inspects tile (t - l), so 32 predecessors cost one
+    // round trip instead of 32
+    uint32_t at = 0, ah = 0;
+    for (int q = lane; q < SCAN_IPT * (SCAN_THREADS / 32); q += 32) { at += (&s_ct[0][0])[q]; ah += (&s_ch[0][0])[q]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { at += __shfl_xor_sync(0xffffffffu, at, o); ah += __shfl_xor_sync(0xffffffffu, ah, o); }
+    const uint64_t agg = (uint64_t)at | ((uint64_t)ah << 31);
     uint64_t excl = 0;
     if (tile == 0) {
-      st_volatile_u64(&state[0], TIE_FLAG_INCL | agg);
+      if (lane == 0) st_volatile_u64(&state[0], TIE_FLAG_INCL | agg);
     } else {
-      st_volatile_u64(&state[tile], TIE_FLAG_AGG | agg);
+      if (lane == 0) st_volatile_u64(&state[tile], TIE_FLAG_AGG | agg);
       int64_t t = (int64_t)tile - 1;
       while (true) {
-        uint64_t s = ld_volatile_u64(&state[t]);
-        uint64_t flag = s & ~TIE_VAL_MASK;
-        if (flag == 0) continue;
-        excl += s & TIE_VAL_MASK;
-        if (flag == TIE_FLAG_INCL) break;
-        t--;
+        const int64_t mine = t - lane;
+        uint64_t sv = mine >= 0 ? ld_volatile_u64(&state[mine]) : TIE_FLAG_INCL;  // before tile 0: inclusive zero
+        const uint64_t flag = sv & ~TIE_VAL_MASK;
+        const uint32_t ready = __ballot_sync(0xffffffffu, flag != 0);
+        const uint32_t incl = __ballot_sync(0xffffffffu, flag == TIE_FLAG_INCL);
+        // usable prefix of the window: lanes 0..k-1 all published, stop at the first inclusive one
+        const uint32_t first_unready = ready == 0xffffffffu ? 32u : (uint32_t)__ffs(~ready) - 1u;
+        const uint32_t first_incl = incl ? (uint32_t)__ffs(incl) - 1u : 32u;
+        const uint32_t take = first_incl < first_unready ? first_incl + 1u : first_unready;  // lanes [0, take)
+        uint64_t v = (uint32_t)lane < take ? (sv & TIE_VAL_MASK) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        t -= take;
+        if (first_incl < first_unready) break;
       }
-      st_volatile_u64(&state[tile], TIE_FLAG_INCL | (excl + agg));
+      if (lane == 0) st_volatile_u64(&state[tile], TIE_FLAG_INCL | (excl + agg));
     }
-    s_base = excl;
-    if ((uint64_t)(tile + 1) * SCAN_TILE >= n) *m_out = (uint32_t)((excl + agg) & 0x7FFFFFFFull);
+    if (lane == 0) {
+      s_base = excl;
+      if ((uint64_t)(tile + 1) * SCAN_TILE >= n) *m_out = (uint32_t)((excl + agg) & 0x7FFFFFFFull);
+    }
   }
   __syncthreads();
   const uint64_t b0 = s_base;

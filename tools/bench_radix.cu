@@ -52,6 +52,12 @@ int main(int argc, char **argv) {
   cudaMemcpy(h.data(), ka + (n > (1u << 20) ? n / 2 : 0), std::min<size_t>(n, 1 << 20) * 4, cudaMemcpyDeviceToHost);
   bool ok = true;
   for (size_t i = 1; i < std::min<size_t>(n, 1 << 20); i++) ok &= h[i - 1] <= h[i];
+#ifdef TEZGPU_RADIX_DEBUG
+  uint32_t rounds = 0;
+  cudaMemcpy(&rounds, ws.tile_counter + 7, 4, cudaMemcpyDeviceToHost);
+  printf("look-back round trips of digit 0 over 4 passes: %u (tiles/pass %u) => %.1f per tile\n", rounds, radix_num_tiles<uint32_t>(n),
+         rounds / 4.0 / radix_num_tiles<uint32_t>(n));
+#endif
   cudaError_t err = cudaGetLastError();
   printf("threads=%d ipt=%d n=%u 4 passes best=%.3f ms (%.3f ms/pass) sorted=%d err=%s\n", TEZGPU_RADIX_THREADS32,
          TEZGPU_RADIX_IPT32, n, best, best / 4, (int)ok, cudaGetErrorString(err));
