@@ -94,6 +94,7 @@ class SortPipeline {
   int *d_error() { return reinterpret_cast<int *>(small.as<uint32_t>() + 2064); }
   uint32_t *d_large() { return small.as<uint32_t>() + 2065; }
   uint32_t *d_m() { return small.as<uint32_t>() + 2072; }
+  unsigned long long *d_ties() { return reinterpret_cast<unsigned long long *>(small.as<uint32_t>() + 2074); }
   uint32_t *d_ticket() { return small.as<uint32_t>() + 2073; }
   unsigned long long *d_dups() { return reinterpret_cast<unsigned long long *>(small.as<uint32_t>() + 2066); }
   uint64_t *d_totals() { return reinterpret_cast<uint64_t *>(small.as<uint32_t>() + 2068); }
@@ -210,31 +211,17 @@ class SortPipeline {
       timer.mark(stream);
 
       // ---------------- ties: records whose sort words collide are ordered by the rest of the key.
-      // One look-back scan compacts them, one comparator kernel orders the (common) small groups; the partition
-      // bounds and -- for fixed-width records -- the segment layout are computed speculatively so that the whole
-      // common path needs a single host round trip (tie count, large groups, duplicates, error flag, layout totals).
-      t_pos[0].ensure(n4); t_gid[0].ensure(n4); t_lidx[0].ensure(n4);  // worst case: every record is tied
-      tie_state.ensure(((size_t)nblk + 1) * 8);
-      TG_CUDA(cudaMemsetAsync(tie_state.p, 0, ((size_t)nblk + 1) * 8, stream));
+      // One streaming kernel finds the groups and orders the (common) small ones in place; the partition bounds and
+      // -- for fixed-width records -- the segment layout are computed speculatively so that the whole common path needs a
+      // single host round trip (tie count, large groups, duplicates, error flag, layout totals).
       const uint32_t depth0 = (uint32_t)((32 - pbits) / 8);
-#ifdef TEZGPU_TIE_LOOKBACK
-      k_tie_scan<<<nblk, SCAN_THREADS, 0, stream>>>(K, order, n, tie_state.as<uint64_t>(), d_ticket(), t_pos[0].as<uint32_t>(),
-                                                    t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>(), d_m());
-      const uint32_t *d_m_ptr = d_m();
-#else
-      // count -> single-block scan of the per-tile counts -> compact; the tied-record count stays on the device
-      k_tie_count<<<nblk, SCAN_THREADS, 0, stream>>>(K, n, blk.as<uint64_t>());
-      k_scan_block_sums<<<1, 1024, 0, stream>>>(blk.as<uint64_t>(), nblk);
-      k_tie_compact<<<nblk, SCAN_THREADS, 0, stream>>>(K, order, n, blk.as<uint64_t>(), t_pos[0].as<uint32_t>(),
-                                                       t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>());
-      launches += 2;
-      const uint32_t *d_m_ptr = reinterpret_cast<const uint32_t *>(blk.as<uint64_t>() + nblk);  // low word = tied records
-#endif
-      k_tie_small<<<(uint32_t)std::min<uint64_t>(div_up(n, 256), (uint64_t)num_sms * 8), 256, 0, stream>>>(
-          rec, t_pos[0].as<uint32_t>(), t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>(), d_m_ptr, depth0, order,
-          same.as<uint8_t>(), d_dups(), d_large());
+      int per_sm_tf = 0;
+      TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tf, k_tie_fix, TIEFIX_THREADS, 0));
+      k_tie_fix<<<(uint32_t)std::min<uint64_t>(div_up(n, TIEFIX_TILE), (uint64_t)num_sms * std::max(per_sm_tf, 1)), TIEFIX_THREADS, 0, stream>>>(
+          rec, K, order, n, depth0, same.as<uint8_t>(), d_dups(), d_large(), d_ties());
+      const uint32_t *d_m_ptr = reinterpret_cast<const uint32_t *>(d_ties());
       k_part_bounds<<<(uint32_t)div_up((uint64_t)P + 1, 256), 256, 0, stream>>>(K, n, P, pbits, part_start.as<uint32_t>());
-      launches += 3;
+      launches += 2;
       state.have_bounds = true;
       state.spec_layout = false;
       if (rec.fixed) {
@@ -259,9 +246,20 @@ class SortPipeline {
       memcpy(&state.spec_file_bytes, hw + 4, 8);
       memcpy(&state.spec_tiles, hw + 6, 8);
       uint64_t *hs = h_small.as<uint64_t>() + 16;
-      if (m && hw[1]) {
+      if (hw[1]) {
         // some group is larger than TIE_SMALL_MAX: radix refinement rounds over all tied records
+        k_tie_count<<<nblk, SCAN_THREADS, 0, stream>>>(K, n, blk.as<uint64_t>());
+        k_scan_block_sums<<<1, 1024, 0, stream>>>(blk.as<uint64_t>(), nblk);
+        TG_CUDA(cudaMemcpyAsync(&hs[0], blk.as<uint64_t>() + nblk, 8, cudaMemcpyDeviceToHost, stream));
+        TG_CUDA(cudaStreamSynchronize(stream));
+        m = (uint32_t)hs[0];
+        tie_records = m;
         for (int s2 = 0; s2 < 2; s2++) { t_pos[s2].ensure((size_t)m * 4); t_gid[s2].ensure((size_t)m * 4); t_lidx[s2].ensure((size_t)m * 4); }
+        k_tie_compact<<<nblk, SCAN_THREADS, 0, stream>>>(K, order, n, blk.as<uint64_t>(), t_pos[0].as<uint32_t>(),
+                                                         t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>());
+        launches += 3;
+        // positions already fixed in place keep their (correct) same[] flags: the rounds below recompute every tied
+        // record anyway, so restart the duplicate count
         TG_CUDA(cudaMemsetAsync(d_dups(), 0, 8, stream));
         uint32_t depth = depth0;
         int cur = 0;

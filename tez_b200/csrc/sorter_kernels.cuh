@@ -359,6 +359,71 @@ __global__ void __launch_bounds__(256)
     tie_small_one(r, pos, gid, lidx, m, j, depth, order, same, dup_count, large_groups);
 }
 
+// ------------------------------------------------------------------------------------------------ in-place tie fix
+// One streaming pass over the sorted sort words finds the head of every group of colliding records; groups of at most
+// TIE_SMALL_MAX records (with uniformly distributed keys: essentially all of them, 2-3 members each) are ordered on the
+// spot by ONE thread with a stable insertion sort under the full RawComparator.  No compaction, no scan, no host round
+// trip.  Larger groups are only counted (-> general refinement path).
+constexpr int TIEFIX_THREADS = 256;
+constexpr int TIEFIX_IPT = 8;
+constexpr int TIEFIX_TILE = TIEFIX_THREADS * TIEFIX_IPT;
+
+__global__ void __launch_bounds__(TIEFIX_THREADS)
+    k_tie_fix(Records r, const uint32_t *__restrict__ K, uint32_t *__restrict__ order, uint32_t n, uint32_t depth,
+              uint8_t *__restrict__ same, unsigned long long *__restrict__ dup_count, uint32_t *__restrict__ large_groups,
+              unsigned long long *__restrict__ tie_records) {
+  __shared__ uint32_t s_heads[TIEFIX_TILE / 2 + 1];
+  __shared__ uint32_t s_nheads;
+  const uint32_t ntiles = (n + TIEFIX_TILE - 1) / TIEFIX_TILE;
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if (threadIdx.x == 0) s_nheads = 0;
+    __syncthreads();
+    const uint32_t base = tile * TIEFIX_TILE;
+    uint32_t kk[TIEFIX_IPT], kp[TIEFIX_IPT], kn[TIEFIX_IPT];
+#pragma unroll
+    for (int q = 0; q < TIEFIX_IPT; q++) {
+      const uint32_t i = base + q * TIEFIX_THREADS + threadIdx.x;
+      kk[q] = i < n ? __ldg(K + i) : 0u;
+      kp[q] = (i > 0 && i < n) ? __ldg(K + i - 1) : ~kk[q];
+      kn[q] = (i + 1 < n) ? __ldg(K + i + 1) : ~kk[q];
+    }
+#pragma unroll
+    for (int q = 0; q < TIEFIX_IPT; q++) {
+      const uint32_t i = base + q * TIEFIX_THREADS + threadIdx.x;
+      if (i < n && kp[q] != kk[q] && kn[q] == kk[q]) s_heads[atomicAdd(&s_nheads, 1u)] = i;
+    }
+    __syncthreads();
+    const uint32_t nh = s_nheads;
+    uint32_t my_dups = 0, my_ties = 0;
+    for (uint32_t hidx = threadIdx.x; hidx < nh; hidx += TIEFIX_THREADS) {
+      const uint32_t i = s_heads[hidx];
+      const uint32_t k = K[i];
+      uint32_t e = i + 2;
+      while (e < n && e - i <= TIE_SMALL_MAX && K[e] == k) e++;
+      const uint32_t sz = e - i;
+      if (sz > TIE_SMALL_MAX) { atomicAdd(large_groups, 1u); continue; }
+      my_ties += sz;
+      uint32_t idx[TIE_SMALL_MAX];
+      for (uint32_t j = 0; j < sz; j++) idx[j] = order[i + j];
+      // stable insertion sort (equal keys keep their original relative order)
+      for (uint32_t a = 1; a < sz; a++) {
+        const uint32_t v = idx[a];
+        uint32_t b = a;
+        while (b > 0 && compare_keys_from(r, idx[b - 1], v, depth) > 0) { idx[b] = idx[b - 1]; b--; }
+        idx[b] = v;
+      }
+      order[i] = idx[0];
+      for (uint32_t j = 1; j < sz; j++) {
+        order[i + j] = idx[j];
+        if (compare_keys_from(r, idx[j - 1], idx[j], depth) == 0) { same[i + j] = 1; my_dups++; }
+      }
+    }
+    if (my_dups) atomicAdd(dup_count, (unsigned long long)my_dups);
+    if (my_ties) atomicAdd(tie_records, (unsigned long long)my_ties);
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ refinement rounds
 // sub-key for the next 3 normalised content bytes at `depth`:
 //   len >  depth : chunk24 << 8 | (128 + min(3, len - depth))
