@@ -160,6 +160,9 @@ typedef struct tezgpu_kv_index {
 
 /* opens the k-way merge over nseg sorted IFile segments: verifies checksums, parses, merges on device */
 int32_t tezgpu_merge_open(const tezgpu_conf *conf, const tezgpu_segment *segs, uint32_t nseg, tezgpu_merger **out);
+/* runs a new merge through an existing handle, keeping its device allocations (the per-step reduce side of the
+ * multi-GPU shuffle; a container-reused task) */
+int32_t tezgpu_merge_reopen(tezgpu_merger *m, const tezgpu_segment *segs, uint32_t nseg);
 /* total records / key+value bytes of the merged stream */
 int32_t tezgpu_merge_counts(tezgpu_merger *m, uint64_t *records, uint64_t *kv_bytes);
 /* replaces the next()/getKey()/getValue()/isSameKey() loop: fills up to idx_cap records (key||value bytes appended to

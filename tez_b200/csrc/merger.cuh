@@ -308,6 +308,7 @@ class Merger {
   void open(const tezgpu_segment *in, uint32_t nseg) {
     cudaStream_t st = pipe.stream;
     TG_CUDA(cudaSetDevice(pipe.conf.device));
+    parsed_fixed = false;
     // ---- segments already on this device are used in place (no copy; kernels handle any byte alignment);
     //      host segments are staged contiguously with 16-byte aligned starts
     segs.resize(nseg);

@@ -26,6 +26,14 @@ int32_t tezgpu_merge_open(const tezgpu_conf *conf, const tezgpu_segment *segs, u
   return TEZGPU_OK;
 }
 
+int32_t tezgpu_merge_reopen(tezgpu_merger *m, const tezgpu_segment *segs, uint32_t nseg) {
+  TG_API_BEGIN
+  TG_CHECK(m && (segs || nseg == 0), TEZGPU_E_INVALID, "null argument");
+  m->m.launches = 0;
+  m->m.open(segs, nseg);
+  TG_API_END
+}
+
 int32_t tezgpu_merge_counts(tezgpu_merger *m, uint64_t *records, uint64_t *kv_bytes) {
   TG_API_BEGIN
   TG_CHECK(m, TEZGPU_E_INVALID, "null handle");

@@ -368,16 +368,47 @@ constexpr int TIEFIX_THREADS = 256;
 constexpr int TIEFIX_IPT = 8;
 constexpr int TIEFIX_TILE = TIEFIX_THREADS * TIEFIX_IPT;
 
+constexpr int TIEFIX_FLUSH = 4 * TIEFIX_THREADS;               // process the collected heads once this many are queued
+constexpr int TIEFIX_CAP = TIEFIX_FLUSH + TIEFIX_TILE / 2 + 8;  // a tile adds at most TILE/2 heads
+
+__device__ __forceinline__ void tie_fix_group(const Records &r, const uint32_t *__restrict__ K, uint32_t *__restrict__ order,
+                                              uint32_t n, uint32_t i, uint32_t depth, uint8_t *__restrict__ same,
+                                              uint32_t &my_dups, uint32_t &my_ties, uint32_t *__restrict__ large_groups) {
+  const uint32_t k = K[i];
+  uint32_t e = i + 2;
+  while (e < n && e - i <= TIE_SMALL_MAX && K[e] == k) e++;
+  const uint32_t sz = e - i;
+  if (sz > TIE_SMALL_MAX) { atomicAdd(large_groups, 1u); return; }
+  my_ties += sz;
+  uint32_t idx[TIE_SMALL_MAX];
+  for (uint32_t j = 0; j < sz; j++) idx[j] = order[i + j];
+  // stable insertion sort (equal keys keep their original relative order)
+  for (uint32_t a = 1; a < sz; a++) {
+    const uint32_t v = idx[a];
+    uint32_t b = a;
+    while (b > 0 && compare_keys_from(r, idx[b - 1], v, depth) > 0) { idx[b] = idx[b - 1]; b--; }
+    idx[b] = v;
+  }
+  order[i] = idx[0];
+  for (uint32_t j = 1; j < sz; j++) {
+    order[i + j] = idx[j];
+    if (compare_keys_from(r, idx[j - 1], idx[j], depth) == 0) { same[i + j] = 1; my_dups++; }
+  }
+}
+
+// The streaming part (all warps) queues group heads in shared memory; once a few hundred are queued every thread takes
+// one, so the latency-bound comparator work runs with the whole CTA instead of one warp.
 __global__ void __launch_bounds__(TIEFIX_THREADS)
     k_tie_fix(Records r, const uint32_t *__restrict__ K, uint32_t *__restrict__ order, uint32_t n, uint32_t depth,
               uint8_t *__restrict__ same, unsigned long long *__restrict__ dup_count, uint32_t *__restrict__ large_groups,
               unsigned long long *__restrict__ tie_records) {
-  __shared__ uint32_t s_heads[TIEFIX_TILE / 2 + 1];
+  __shared__ uint32_t s_heads[TIEFIX_CAP];
   __shared__ uint32_t s_nheads;
   const uint32_t ntiles = (n + TIEFIX_TILE - 1) / TIEFIX_TILE;
+  if (threadIdx.x == 0) s_nheads = 0;
+  __syncthreads();
+  uint32_t my_dups = 0, my_ties = 0;
   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    if (threadIdx.x == 0) s_nheads = 0;
-    __syncthreads();
     const uint32_t base = tile * TIEFIX_TILE;
     uint32_t kk[TIEFIX_IPT], kp[TIEFIX_IPT], kn[TIEFIX_IPT];
 #pragma unroll
@@ -394,34 +425,17 @@ __global__ void __launch_bounds__(TIEFIX_THREADS)
     }
     __syncthreads();
     const uint32_t nh = s_nheads;
-    uint32_t my_dups = 0, my_ties = 0;
-    for (uint32_t hidx = threadIdx.x; hidx < nh; hidx += TIEFIX_THREADS) {
-      const uint32_t i = s_heads[hidx];
-      const uint32_t k = K[i];
-      uint32_t e = i + 2;
-      while (e < n && e - i <= TIE_SMALL_MAX && K[e] == k) e++;
-      const uint32_t sz = e - i;
-      if (sz > TIE_SMALL_MAX) { atomicAdd(large_groups, 1u); continue; }
-      my_ties += sz;
-      uint32_t idx[TIE_SMALL_MAX];
-      for (uint32_t j = 0; j < sz; j++) idx[j] = order[i + j];
-      // stable insertion sort (equal keys keep their original relative order)
-      for (uint32_t a = 1; a < sz; a++) {
-        const uint32_t v = idx[a];
-        uint32_t b = a;
-        while (b > 0 && compare_keys_from(r, idx[b - 1], v, depth) > 0) { idx[b] = idx[b - 1]; b--; }
-        idx[b] = v;
-      }
-      order[i] = idx[0];
-      for (uint32_t j = 1; j < sz; j++) {
-        order[i + j] = idx[j];
-        if (compare_keys_from(r, idx[j - 1], idx[j], depth) == 0) { same[i + j] = 1; my_dups++; }
-      }
+    const bool last = tile + gridDim.x >= ntiles;
+    if (nh >= (uint32_t)TIEFIX_FLUSH || last) {
+      for (uint32_t hidx = threadIdx.x; hidx < nh; hidx += TIEFIX_THREADS)
+        tie_fix_group(r, K, order, n, s_heads[hidx], depth, same, my_dups, my_ties, large_groups);
+      __syncthreads();
+      if (threadIdx.x == 0) s_nheads = 0;
+      __syncthreads();
     }
-    if (my_dups) atomicAdd(dup_count, (unsigned long long)my_dups);
-    if (my_ties) atomicAdd(tie_records, (unsigned long long)my_ties);
-    __syncthreads();
   }
+  if (my_dups) atomicAdd(dup_count, (unsigned long long)my_dups);
+  if (my_ties) atomicAdd(tie_records, (unsigned long long)my_ties);
 }
 
 // ------------------------------------------------------------------------------------------------ refinement rounds

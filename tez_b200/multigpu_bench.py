@@ -33,6 +33,7 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
     d_merged = torch.empty(int(cap * 1.3) + (1 << 20), dtype=torch.uint8, device=dev)
     p0, p1 = shuffle.owner_ranges(P, world)[rank]
     launches = [0]
+    merger = [None]
     phase_ms = {"sort": [], "exchange": [], "merge": []}
 
     def step(timed):
@@ -43,12 +44,16 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
         recv, segs = shuffle.exchange_partitions(d_out[:out_len], index, P)
         e[2].record()
         base = recv.data_ptr()
-        m = T.GpuMerger([(base + off, ln) for off, ln, _, _ in segs], comparator=T.CMP_BYTES, device=local,
-                        device_ptrs=True, fixed=(KEY_LEN, VAL_LEN), partitions=[p for _, _, p, _ in segs],
-                        num_partitions=p1 - p0)
+        seg_list = [(base + off, ln) for off, ln, _, _ in segs]
+        parts = [p for _, _, p, _ in segs]
+        if merger[0] is None:
+            merger[0] = T.GpuMerger(seg_list, comparator=T.CMP_BYTES, device=local, device_ptrs=True,
+                                    fixed=(KEY_LEN, VAL_LEN), partitions=parts, num_partitions=p1 - p0)
+        else:
+            merger[0].reopen(seg_list, parts)
+        m = merger[0]
         mlen, mindex, mst = m.write_partitions_device(d_merged.data_ptr(), d_merged.numel())
         nrec, _ = m.counts()
-        m.close()
         e[3].record()
         if timed:
             torch.cuda.synchronize()

@@ -122,11 +122,17 @@ class GpuMerger:
         self.conf = make_conf(num_partitions, comparator=comparator, partitioner=PART_GIVEN, device=device, fixed=fixed,
                               send_empty=send_empty)
         self.P = num_partitions
+        self._has_header, self._device_ptrs = has_header, device_ptrs
+        arr = self._segments(segments, partitions)
+        self.h = C.c_void_p()
+        check(self.L.tezgpu_merge_open(C.byref(self.conf), arr, len(segments), C.byref(self.h)))
+
+    def _segments(self, segments, partitions):
         self._keep = []
         arr = (Segment * max(1, len(segments)))()
-        flags = (SEG_HAS_HEADER if has_header else 0) | (SEG_DEVICE if device_ptrs else 0)
+        flags = (SEG_HAS_HEADER if self._has_header else 0) | (SEG_DEVICE if self._device_ptrs else 0)
         for i, s in enumerate(segments):
-            if device_ptrs:
+            if self._device_ptrs:
                 arr[i].data, arr[i].len = s
             else:
                 a = np.ascontiguousarray(np.frombuffer(s, dtype=np.uint8) if isinstance(s, (bytes, bytearray)) else s)
@@ -135,8 +141,12 @@ class GpuMerger:
                 arr[i].len = a.size
             arr[i].flags = flags
             arr[i].partition = 0 if partitions is None else int(partitions[i])
-        self.h = C.c_void_p()
-        check(self.L.tezgpu_merge_open(C.byref(self.conf), arr, len(segments), C.byref(self.h)))
+        return arr
+
+    def reopen(self, segments, partitions=None):
+        """New merge through the same handle (device allocations are kept)."""
+        arr = self._segments(segments, partitions)
+        check(self.L.tezgpu_merge_reopen(self.h, arr, len(segments)))
 
     def close(self):
         if self.h:
