@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -129,7 +129,7 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = min(host_cores(), 64)
+    cores = min(host_cores(), 128)
     per_task = args.cpu_records_per_task
     partitions = 64 if args.gpus == 1 else 1024
     value, secs, n = run_cpu(cores, per_task, args.steps, args.warmup, partitions)
@@ -211,7 +211,7 @@ def single_gpu(args):
     emit = sum(emit_ms) / len(emit_ms)
     achieved = n * ALGO_BYTES_PER_RECORD / (emit * 1e-3) / 1e9
     traffic = load_traffic()
-    roofline = {"bound": "hbm", "kernel": "k_emit<true> (gather + IFile framing + CRC32 + coalesced store)",
+    roofline = {"bound": "hbm", "kernel": "k_emit_fast<5,true> (gather + IFile framing + CRC32 + coalesced store)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_RECORD, "ms_per_launch": round(emit, 4)}
@@ -266,7 +266,7 @@ def single_gpu(args):
         del h_kv, h_outs
 
     # ---- CPU baseline on this box's host cores (bounded sample)
-    cores = min(host_cores(), 64)
+    cores = min(host_cores(), 128)
     cval, csecs, cn = run_cpu(cores, args.cpu_records_per_task, 1, 0, P)
     cpu = {"value": round(cval, 4), "unit": "GB/s", "cores": cores, "kind": "port",
            "sample": "%d records (%d per task x %d PipelinedSorter tasks), %.2f s" % (cn, args.cpu_records_per_task, cores, csecs)}
