@@ -24,6 +24,10 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
     local = int(os.environ.get("LOCAL_RANK", str(rank)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # point-to-point (send/recv) all-to-all: let NCCL use many channels per peer over NVLink
+    os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "32")
+    os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
+    os.environ.setdefault("NCCL_NCHANNELS_PER_PEER", "32")
     dist.init_process_group("nccl", device_id=dev)
     n, P = args.records, 1024
     d_kv = synth.gen_c2(rank * n, n, seed=4, device=dev)
@@ -43,6 +47,8 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
         e[1].record()
         recv, segs = shuffle.exchange_partitions(d_out[:out_len], index, P)
         e[2].record()
+        # the library works on its own stream: the received bytes must have landed before it reads them
+        torch.cuda.current_stream().synchronize()
         base = recv.data_ptr()
         seg_list = [(base + off, ln) for off, ln, _, _ in segs]
         parts = [p for _, _, p, _ in segs]
