@@ -188,6 +188,30 @@ int32_t tezgpu_merge_write_partitions(tezgpu_merger *m, const char *out_path, co
 void *tezgpu_merge_stream(tezgpu_merger *m);
 int32_t tezgpu_merge_close(tezgpu_merger *m);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Shuffle transfer between the GPUs of one box (NVLink / NVSwitch).
+ * Replaces the ShuffleHandler HTTP GET + FetcherOrderedGrouped.copyMapOutput round trip
+ * (OG/FetcherOrderedGrouped.java:437-632, OG/ShuffleScheduler.java:1370-1470): the producer keeps file.out in an
+ * exportable device buffer, the consumer maps it (CUDA IPC) and pulls the byte ranges of its partitions with one
+ * kernel running on every SM.  Handles are 64 opaque bytes the host layer ships with the DataMovementEvent.
+ * --------------------------------------------------------------------------------------------------------------- */
+#define TEZGPU_PEER_HANDLE_BYTES 64
+/* device buffer another process on the same box may map; *handle_out receives the 64-byte export handle */
+int32_t tezgpu_peer_alloc(int32_t device, uint64_t bytes, void **dptr, uint8_t *handle_out);
+int32_t tezgpu_peer_free(int32_t device, void *dptr);
+/* maps a buffer exported by another process (any device of the box) into this process; enables peer access */
+int32_t tezgpu_peer_open(int32_t device, const uint8_t *handle, void **dptr);
+int32_t tezgpu_peer_close(int32_t device, void *dptr);
+typedef struct tezgpu_copy_range {
+  const void *src;                 /* device address (local, or a peer mapping from tezgpu_peer_open) */
+  void *dst;                       /* device address on `device`; fastest when (dst - src) is a multiple of 16 */
+  uint64_t len;
+} tezgpu_copy_range;
+/* copies n ranges with one launch on `stream` (a cudaStream_t, NULL = the legacy default stream) and returns once
+ * the bytes have landed */
+int32_t tezgpu_fetch_ranges(int32_t device, const tezgpu_copy_range *ranges, uint32_t n, void *stream,
+                            float *ms_kernel);
+
 /* diagnostics: host-side emulation of the device's tiled CRC algebra (same tables, no GPU needed) */
 uint32_t tezgpu_debug_crc_emulate(const uint8_t *body, uint64_t len, uint32_t piece_bytes, uint32_t lead);
 

@@ -179,3 +179,20 @@ def test_batched_multi_partition_merge_matches_per_partition_oracle():
             assert out[start:start + part] == exp
             off += part
         assert off == n
+
+
+def test_merger_reopen_and_large_runs_through_the_staged_parser():
+    """Few large runs (the staged warp parser walks ~1e5 records per segment) and handle reuse."""
+    rng = random.Random(77)
+    segs = []
+    for s in range(3):
+        keys = sorted({rng.getrandbits(48).to_bytes(6, "big") + bytes([s]) for _ in range(40000)})
+        segs.append(O.write_ifile([(k, (zlib.crc32(k) & 0xFFFF).to_bytes(2, "big") * (1 + k[0] % 3)) for k in keys])[0])
+    exp = O.merge(segs, O.CMP_BYTES, factor=100)
+    with T.GpuMerger(segs[:1], comparator=T.CMP_BYTES) as m:
+        first, _, _, _ = m.write_ifile()
+        assert first == O.merge(segs[:1], O.CMP_BYTES)["ifile"]
+        m.reopen(segs)
+        seg, raw, part, _ = m.write_ifile()
+        assert seg == exp["ifile"]
+        assert m.counts()[0] == len(exp["records"])

@@ -233,3 +233,30 @@ def test_crc_of_every_segment_matches_zlib():
         seg = out[start:start + part]
         assert seg[:4] == b"TIF\x00" and raw == part - 4
         assert int.from_bytes(seg[-4:], "big") == zlib.crc32(seg[4:-4])
+
+
+@pytest.mark.parametrize("kl,vl", [(8, 8), (16, 16), (4, 12), (16, 32), (24, 72), (16, 112)])
+@pytest.mark.parametrize("n", [1, 255, 70001])
+def test_fast_emit_other_16_byte_strides(kl, vl, n):
+    """The source-oriented emit kernel serves every fixed-width record whose stride is a multiple of 16 bytes
+    (1..8 pieces per record, tiles of fewer than 256 records for the wide ones)."""
+    rng = np.random.default_rng(kl * 1000 + vl + n)
+    P = 5
+    kv = rng.integers(0, 256, size=n * (kl + vl), dtype=np.uint8)
+    ko = np.arange(n, dtype=np.uint64) * (kl + vl)
+    exp = O.pipelined_sort(O.sorter_conf(P), kv, ko, np.full(n, kl, np.uint32), np.full(n, vl, np.uint32))
+    with T.GpuSorter(P, fixed=(kl, vl)) as s:
+        s.collect_fixed(kv)
+        out, index_bytes, _, st = s.flush_to_memory()
+    assert bytes(out) == exp["file_out"] and index_bytes == exp["index_out"]
+
+
+def test_sorter_handle_reset_reuses_allocations():
+    with T.GpuSorter(4, fixed=(16, 64)) as s:
+        for seed, n in ((1, 5000), (2, 12000), (3, 100)):
+            kv = O.gen_c2(0, n, seed=seed)
+            s.reset()
+            s.collect_fixed(kv)
+            out, index_bytes, _, _ = s.flush_to_memory()
+            exp = O.pipelined_sort_fixed(O.sorter_conf(4), kv, 16, 64)
+            assert bytes(out) == exp["file_out"] and index_bytes == exp["index_out"]

@@ -30,6 +30,10 @@ class Segment(C.Structure):
     _fields_ = [("data", C.c_void_p), ("len", C.c_uint64), ("flags", C.c_uint32), ("partition", C.c_uint32)]
 
 
+class CopyRange(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("len", C.c_uint64)]
+
+
 class KvIndex(C.Structure):
     _fields_ = [("key_off", C.c_uint32), ("key_len", C.c_uint32), ("val_off", C.c_uint32), ("val_len", C.c_uint32),
                 ("same_key", C.c_uint32)]
@@ -62,6 +66,11 @@ SYMBOLS = [
     ("tezgpu_merge_write_partitions_device", C.c_int32, [_V, _V, C.c_uint64, C.c_int32, _P(C.c_uint64), _V, _P(Stats)]),
     ("tezgpu_merge_write_partitions", C.c_int32, [_V, C.c_char_p, C.c_char_p, C.c_int32, _V, _P(Stats)]),
     ("tezgpu_merge_stream", _V, [_V]),
+    ("tezgpu_peer_alloc", C.c_int32, [C.c_int32, C.c_uint64, _P(_V), _V]),
+    ("tezgpu_peer_free", C.c_int32, [C.c_int32, _V]),
+    ("tezgpu_peer_open", C.c_int32, [C.c_int32, _V, _P(_V)]),
+    ("tezgpu_peer_close", C.c_int32, [C.c_int32, _V]),
+    ("tezgpu_fetch_ranges", C.c_int32, [C.c_int32, _P(CopyRange), C.c_uint32, _V, _P(C.c_float)]),
     ("tezgpu_merge_close", C.c_int32, [_V]),
 ]
 

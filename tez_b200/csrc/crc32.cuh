@@ -79,6 +79,34 @@ static inline void crc_build_tables(CrcTables &t, int stride_words) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------- warp-resident maps
+// Every step of the interleaved checksum is a GF(2)-linear map of a 32-bit word ("multiply by a fixed power of x"),
+// classically four 256-entry table look-ups in shared memory.  Random byte values make those look-ups collide on
+// banks (measured: 58 % of the emit kernel's shared-load wavefronts were replays).  The same map split into seven
+// 5-bit digits needs only 32-entry tables, and a 32-entry table is exactly one register across the lanes of a warp:
+// digit k of x selects lane (x >> 5k) & 31 of register t[k] with one SHFL -- no shared memory, no conflicts.
+// All 32 lanes must execute apply() together (lanes with nothing to fold pass 0, which maps to 0).
+struct WarpLinearMap {
+  uint32_t t[7];
+  // f(v) must be the linear map evaluated with any method (byte tables); lane l keeps f(l << 5k)
+  template <typename F>
+  __device__ __forceinline__ void init(F f, uint32_t lane) {
+#pragma unroll
+    for (int k = 0; k < 7; k++) t[k] = f(k < 6 ? lane << (5 * k) : (lane & 3u) << 30);
+  }
+  __device__ __forceinline__ uint32_t apply(uint32_t x) const {
+    // shfl.idx reads b[4:0] of the source-lane operand: no masking needed
+    uint32_t r0 = __shfl_sync(0xffffffffu, t[0], (int)x);
+    uint32_t r1 = __shfl_sync(0xffffffffu, t[1], (int)(x >> 5));
+    uint32_t r2 = __shfl_sync(0xffffffffu, t[2], (int)(x >> 10));
+    uint32_t r3 = __shfl_sync(0xffffffffu, t[3], (int)(x >> 15));
+    uint32_t r4 = __shfl_sync(0xffffffffu, t[4], (int)(x >> 20));
+    uint32_t r5 = __shfl_sync(0xffffffffu, t[5], (int)(x >> 25));
+    uint32_t r6 = __shfl_sync(0xffffffffu, t[6], (int)(x >> 30));
+    return (r0 ^ r1 ^ r2) ^ (r3 ^ r4 ^ r5) ^ r6;
+  }
+};
+
 // crc * x^(8*nbytes) for nbytes < 2^36
 __device__ __forceinline__ uint32_t crc_shift_bytes(const CrcTables *__restrict__ t, uint32_t crc, uint64_t nbytes) {
   uint32_t a0 = (uint32_t)(nbytes & 4095), a1 = (uint32_t)((nbytes >> 12) & 4095), a2 = (uint32_t)((nbytes >> 24) & 4095);

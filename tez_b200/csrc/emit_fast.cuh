@@ -135,6 +135,10 @@ struct FastEmitParams {
   uint32_t stride;
 };
 
+#ifndef TEZGPU_CRC_SHFL
+#define TEZGPU_CRC_SHFL 1
+#endif
+
 template <int UNROLL, bool ALIGNED>
 __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT_MIN_CTAS) k_emit_fast(FastEmitParams fp) {
   __shared__ __align__(16) uint8_t s_img[FE_IMG_BYTES];
@@ -154,6 +158,16 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT_MIN_CTAS) k_emit_fast(
   }
   // constant alignment multipliers: x^(32*(31-lane)) for the final in-warp fold
   const uint32_t lane_pow = e.crc->pow_word[4 * (31 - lane)];
+#if TEZGPU_CRC_SHFL
+  // the two maps of the chunk-interleaved checksum as warp-resident 5-bit digit tables (crc32.cuh): "next word"
+  // (* x^32) and "skip to this thread's next chunk" (* x^(32*(4*FE_THREADS-3))), built from the global byte tables
+  WarpLinearMap m_word, m_skip;
+  {
+    const uint32_t *gt = &e.crc->slice[0][0], *ga = &e.crc->advc[0][0];
+    m_word.init([&](uint32_t x) { return gt[768 + (x & 0xFF)] ^ gt[512 + ((x >> 8) & 0xFF)] ^ gt[256 + ((x >> 16) & 0xFF)] ^ gt[x >> 24]; }, lane);
+    m_skip.init([&](uint32_t x) { return ga[x & 0xFF] ^ ga[256 + ((x >> 8) & 0xFF)] ^ ga[512 + ((x >> 16) & 0xFF)] ^ ga[768 + (x >> 24)]; }, lane);
+  }
+#endif
   const uint32_t img_base = (uint32_t)__cvta_generic_to_shared(s_img);
   const uint8_t *__restrict__ kv = e.rec.kv;
   const uint8_t *kv_end = kv + e.rec.kv_bytes;
@@ -259,6 +273,36 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT_MIN_CTAS) k_emit_fast(
       uint32_t c = 0;
       if (cz > ca) {
         const uint32_t Cn = cz - ca;
+#if TEZGPU_CRC_SHFL
+        // uniform trip count for the whole CTA (the maps are warp collectives); a thread whose chunk index is still
+        // negative folds zeros, which stay zero
+        const uint32_t iters = (Cn + FE_THREADS - 1) / FE_THREADS;
+        const int32_t last_i = (int32_t)Cn - FE_THREADS + tid;
+        int32_t i = last_i - (int32_t)(iters - 1) * FE_THREADS;
+        for (uint32_t it = 0; it < iters; it++, i += FE_THREADS) {
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (i >= 0) {
+            const uint32_t b0 = 16u * (ca + (uint32_t)i);
+            v = *reinterpret_cast<const uint4 *>(s_img + b0);
+            if (b0 >= lead) stg_stream_v4(dstg + b0, v);
+            else for (uint32_t x = lead; x < b0 + 16u; x++) dstg[x] = s_img[x];  // ragged first chunk of the tile
+            if (i == 0 && (cb0 & 15u)) {  // zero the bytes before the body (segment header / previous tile's bytes)
+              const uint32_t skip = cb0 & 15u;
+              uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (uint32_t k = 0; k < 4; k++) {
+                if (skip >= 4 * k + 4) w[k] = 0;
+                else if (skip > 4 * k) w[k] &= 0xFFFFFFFFu << (8u * (skip - 4 * k));
+              }
+              v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+          uint32_t x = m_word.apply(c ^ v.x) ^ v.y;
+          x = m_word.apply(x) ^ v.z;
+          x = m_word.apply(x) ^ v.w;
+          c = (it + 1 == iters) ? m_word.apply(x) : m_skip.apply(x);
+        }
+#else
         if (Cn + tid >= FE_THREADS) {
           const uint32_t last_i = Cn - FE_THREADS + tid;
           for (uint32_t i = last_i % FE_THREADS; i <= last_i; i += FE_THREADS) {
@@ -287,6 +331,7 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT_MIN_CTAS) k_emit_fast(
             else c = s_adv[x & 0xFF] ^ s_adv[256 + ((x >> 8) & 0xFF)] ^ s_adv[512 + ((x >> 16) & 0xFF)] ^ s_adv[768 + (x >> 24)];
           }
         }
+#endif
       }
       s_part[tid] = c;
       // chunks outside [ca, cz): the tile's leading header-only chunk (cannot happen: header and body share chunk ca

@@ -28,12 +28,17 @@ constexpr int CRCV_THREADS = 256;
 __global__ void __launch_bounds__(CRCV_THREADS)
     k_crc_pieces(const uint8_t *__restrict__ data, const SegDesc *__restrict__ segs, const uint32_t *__restrict__ piece_start,
                  uint32_t nseg, const CrcTables *__restrict__ t, TileCrc *__restrict__ out) {
-  __shared__ uint32_t s_tab[4 * 256], s_adv[4 * 256], s_adv32[4 * 256], s_part[CRCV_THREADS];
+  static_assert(CRCV_THREADS == EMIT_CRC_STRIDE_WORDS, "advc is built for this chunk interleave");
+  __shared__ uint32_t s_tab[256], s_adv128[4 * 256], s_part[CRCV_THREADS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < 4 * 256; i += CRCV_THREADS) {
-    s_tab[i] = (&t->slice[0][0])[i];
-    s_adv[i] = (&t->adv[0][0])[i];
-    s_adv32[i] = (&t->adv32[0][0])[i];
+  s_tab[tid] = t->slice[0][tid];
+  for (int i = tid; i < 4 * 256; i += CRCV_THREADS) s_adv128[i] = (&t->adv128[0][0])[i];
+  // the two maps of the 16-byte-chunk interleave as warp-resident digit tables (crc32.cuh)
+  WarpLinearMap m_word, m_skip;
+  {
+    const uint32_t *gt = &t->slice[0][0], *ga = &t->advc[0][0];
+    m_word.init([&](uint32_t x) { return gt[768 + (x & 0xFF)] ^ gt[512 + ((x >> 8) & 0xFF)] ^ gt[256 + ((x >> 16) & 0xFF)] ^ gt[x >> 24]; }, lane);
+    m_skip.init([&](uint32_t x) { return ga[x & 0xFF] ^ ga[256 + ((x >> 8) & 0xFF)] ^ ga[512 + ((x >> 16) & 0xFF)] ^ ga[768 + (x >> 24)]; }, lane);
   }
   const uint32_t piece = blockIdx.x;
   uint32_t lo = 0, hi = nseg;  // last segment with piece_start[s] <= piece
@@ -45,46 +50,56 @@ __global__ void __launch_bounds__(CRCV_THREADS)
   const uint64_t body_bytes = sd.body_end - sd.body0;
   const uint64_t a = (uint64_t)(piece - piece_start[lo]) * CRC_PIECE;
   const uint64_t b = min(body_bytes, a + CRC_PIECE);
-  // piece = body bytes [a, b); word-aligned window [wlo, whi) around it: leading bytes of the first word that precede
-  // the piece are masked to zero (a remainder with zero initial value ignores leading zeros), trailing bytes are
-  // folded in bytewise by lane 0
+  // piece = body bytes [a, b) seen as 16-byte chunks from the aligned-down address: bytes of the first chunk that
+  // precede the piece are masked to zero (a remainder with zero initial value ignores leading zeros), the trailing
+  // partial chunk is folded bytewise by lane 0.  Thread t owns the chunks whose distance from the last whole chunk is
+  // == T-1-t (mod T): 3 x "next word" and one "skip to my next chunk" per chunk, partials aligned by a constant.
   const uint8_t *base = data + sd.off + sd.body0;
   const uint8_t *pa = base + a, *pb = base + b;
-  const uint32_t mis = (uint32_t)((uintptr_t)pa & 3u);
-  const uint32_t *w32 = reinterpret_cast<const uint32_t *>(pa - mis);
-  const uint32_t W = (uint32_t)(((pb - (pa - mis))) >> 2);  // whole words starting at the aligned-down address
-  const uint32_t head_mask = 0xFFFFFFFFu << (8u * mis);
-  __syncthreads();
+  const uint32_t mis = (uint32_t)((uintptr_t)pa & 15u);
+  const uint4 *c16 = reinterpret_cast<const uint4 *>(pa - mis);
+  const uint32_t Cn = (uint32_t)((pb - (pa - mis)) >> 4);  // whole chunks
   uint32_t c = 0;
-  if (W + tid >= CRCV_THREADS && W > 0) {
-    const uint32_t last_i = W - CRCV_THREADS + tid;
-    uint32_t i = last_i % CRCV_THREADS;
-    for (; i < last_i; i += CRCV_THREADS) {
-      uint32_t w = w32[i];
-      if (i == 0) w &= head_mask;
-      uint32_t x = c ^ w;
-      c = s_adv[x & 0xFF] ^ s_adv[256 + ((x >> 8) & 0xFF)] ^ s_adv[512 + ((x >> 16) & 0xFF)] ^ s_adv[768 + (x >> 24)];
+  if (Cn) {
+    const uint32_t iters = (Cn + CRCV_THREADS - 1) / CRCV_THREADS;
+    const int32_t last_i = (int32_t)Cn - CRCV_THREADS + tid;
+    int32_t i = last_i - (int32_t)(iters - 1) * CRCV_THREADS;
+    for (uint32_t it = 0; it < iters; it++, i += CRCV_THREADS) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (i >= 0) {
+        v = c16[i];
+        if (i == 0 && mis) {
+          uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (uint32_t k = 0; k < 4; k++) {
+            if (mis >= 4 * k + 4) w[k] = 0;
+            else if (mis > 4 * k) w[k] &= 0xFFFFFFFFu << (8u * (mis - 4 * k));
+          }
+          v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+      uint32_t x = m_word.apply(c ^ v.x) ^ v.y;
+      x = m_word.apply(x) ^ v.z;
+      x = m_word.apply(x) ^ v.w;
+      c = (it + 1 == iters) ? m_word.apply(x) : m_skip.apply(x);
     }
-    uint32_t w = w32[last_i];
-    if (last_i == 0) w &= head_mask;
-    uint32_t x = c ^ w;
-    c = s_tab[768 + (x & 0xFF)] ^ s_tab[512 + ((x >> 8) & 0xFF)] ^ s_tab[256 + ((x >> 16) & 0xFF)] ^ s_tab[x >> 24];
   }
   s_part[tid] = c;
   __syncthreads();
   if (warp == 0) {
+    // lane l folds partials l, l+32, ... (Horner with x^(128*32)), aligns by x^(128*(31-l)), xor-reduce
     uint32_t q = 0;
 #pragma unroll
     for (int k = 0; k < CRCV_THREADS / 32; k++) {
-      q = s_adv32[q & 0xFF] ^ s_adv32[256 + ((q >> 8) & 0xFF)] ^ s_adv32[512 + ((q >> 16) & 0xFF)] ^ s_adv32[768 + (q >> 24)];
+      q = s_adv128[q & 0xFF] ^ s_adv128[256 + ((q >> 8) & 0xFF)] ^ s_adv128[512 + ((q >> 16) & 0xFF)] ^ s_adv128[768 + (q >> 24)];
       q ^= s_part[lane + 32 * k];
     }
-    q = crc_multmodp(q, t->pow_word[31 - lane]);
+    q = crc_multmodp(q, t->pow_word[4 * (31 - lane)]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q ^= __shfl_xor_sync(0xffffffffu, q, o);
     if (lane == 0) {
       uint32_t raw = q;
-      const uint8_t *tail = (W > 0) ? (pa - mis) + 4ull * W : pa;  // W == 0: fewer than a word, all bytewise
+      const uint8_t *tail = Cn ? (pa - mis) + 16ull * Cn : pa;  // no whole chunk: everything bytewise
       for (const uint8_t *x = tail; x < pb; x++) raw = s_tab[(raw ^ *x) & 0xFF] ^ (raw >> 8);
       TileCrc tc;
       tc.raw = raw;

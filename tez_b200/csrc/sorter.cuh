@@ -8,7 +8,7 @@
 
 #include "../../include/tezgpu.h"
 #include "device_util.h"
-#include "emit_fast.cuh"
+#include "emit_pipe.cuh"
 #include "sorter_kernels.cuh"
 
 namespace tezgpu {
@@ -417,6 +417,11 @@ class SortPipeline {
           }
           uint32_t grid = (uint32_t)std::min<uint64_t>(div_up(tiles, FE3_SUBS), (uint64_t)num_sms);
           k_emit_fast3<5><<<grid, FE3_THREADS, FE3_SMEM, stream>>>(fp);
+        } else if (fast_aligned && (uint64_t)e.recs_per_tile * fp.cpr <= 5u * FE_THREADS && !getenv("TEZGPU_EMIT_V2")) {
+          // software-pipelined kernel (emit_pipe.cuh): a tile's pieces must fit the registers of one gather round
+          TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_fast4<5>, FE_THREADS, 0));
+          uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));
+          k_emit_fast4<5><<<grid, FE_THREADS, 0, stream>>>(fp);
         } else if (fast_aligned) {
           TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_fast<5, true>, FE_THREADS, 0));
           uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));

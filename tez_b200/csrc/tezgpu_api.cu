@@ -10,6 +10,7 @@
 #include "../../include/tezgpu.h"
 #include "merger.cuh"
 #include "sorter.cuh"
+#include "peer_fetch.cuh"
 
 using namespace tezgpu;
 
@@ -309,6 +310,95 @@ int32_t tezgpu_sorter_sort_device_fixed(tezgpu_sorter *h, const void *d_kv, cons
 }
 
 void *tezgpu_sorter_stream(tezgpu_sorter *h) { return h ? (void *)h->pipe.stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------------ NVLink peer fetch
+int32_t tezgpu_peer_alloc(int32_t device, uint64_t bytes, void **dptr, uint8_t *handle_out) {
+  TG_API_BEGIN
+  TG_CHECK(dptr && handle_out && bytes, TEZGPU_E_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == TEZGPU_PEER_HANDLE_BYTES, "export handle size");
+  TG_CUDA(cudaSetDevice(device));
+  void *p = nullptr;
+  TG_CUDA(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    TG_CUDA(e);
+  }
+  memcpy(handle_out, &h, sizeof(h));
+  *dptr = p;
+  TG_API_END
+}
+
+int32_t tezgpu_peer_free(int32_t device, void *dptr) {
+  TG_API_BEGIN
+  TG_CUDA(cudaSetDevice(device));
+  if (dptr) TG_CUDA(cudaFree(dptr));
+  TG_API_END
+}
+
+int32_t tezgpu_peer_open(int32_t device, const uint8_t *handle, void **dptr) {
+  TG_API_BEGIN
+  TG_CHECK(handle && dptr, TEZGPU_E_INVALID, "null argument");
+  TG_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void *p = nullptr;
+  TG_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *dptr = p;
+  TG_API_END
+}
+
+int32_t tezgpu_peer_close(int32_t device, void *dptr) {
+  TG_API_BEGIN
+  TG_CUDA(cudaSetDevice(device));
+  if (dptr) TG_CUDA(cudaIpcCloseMemHandle(dptr));
+  TG_API_END
+}
+
+int32_t tezgpu_fetch_ranges(int32_t device, const tezgpu_copy_range *ranges, uint32_t n, void *stream, float *ms_kernel) {
+  TG_API_BEGIN
+  TG_CHECK(ranges || n == 0, TEZGPU_E_INVALID, "null argument");
+  if (ms_kernel) *ms_kernel = 0;
+  if (n == 0) return TEZGPU_OK;
+  TG_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<FetchRange> fr(n);
+  uint64_t chunks = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    TG_CHECK((ranges[i].src && ranges[i].dst) || ranges[i].len == 0, TEZGPU_E_INVALID, "null range");
+    fr[i].src = (const uint8_t *)ranges[i].src;
+    fr[i].dst = (uint8_t *)ranges[i].dst;
+    fr[i].len = ranges[i].len;
+    fr[i].chunk0 = chunks;
+    chunks += fetch_chunks(ranges[i].src, ranges[i].dst, ranges[i].len);
+  }
+  if (chunks == 0) return TEZGPU_OK;
+  FetchRange *d_fr = nullptr;
+  TG_CUDA(cudaMalloc(&d_fr, (size_t)n * sizeof(FetchRange)));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t err = cudaMemcpyAsync(d_fr, fr.data(), (size_t)n * sizeof(FetchRange), cudaMemcpyHostToDevice, st);
+  if (err == cudaSuccess && ms_kernel) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+  }
+  if (err == cudaSuccess) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(chunks, (uint64_t)sms * 2);
+    k_fetch_ranges<<<grid, FETCH_THREADS, 0, st>>>(d_fr, n, chunks);
+    err = cudaGetLastError();
+  }
+  if (err == cudaSuccess && ms_kernel) cudaEventRecord(e1, st);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+  if (err == cudaSuccess && ms_kernel) cudaEventElapsedTime(ms_kernel, e0, e1);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  cudaFree(d_fr);
+  TG_CUDA(err);
+  TG_API_END
+}
 
 // Host emulation of the emit kernel's parallel CRC scheme (interleaved per-thread streams over the 4-byte words of a
 // piece, power-table alignment, xor-fold of piece contributions into the segment remainder, final conditioning).

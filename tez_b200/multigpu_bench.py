@@ -31,26 +31,42 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
     dist.init_process_group("nccl", device_id=dev)
     n, P = args.records, 1024
     d_kv = synth.gen_c2(rank * n, n, seed=4, device=dev)
+    torch.cuda.synchronize()   # the library works on its own stream
     sorter = T.GpuSorter(P, fixed=(KEY_LEN, VAL_LEN), device=local)
     cap = n * OUT_REC + 10 * P + 4096
-    d_out = torch.empty(cap, dtype=torch.uint8, device=dev)
+    # shuffle transport: "peer" = consumers pull file.out ranges out of the producers' HBM with libtezgpu's fetch kernel
+    # (CUDA IPC mappings over NVLink); "nccl" = one variable-size all-to-all of NCCL send/recv pairs (the baseline)
+    transport = os.environ.get("TEZ_SHUFFLE", "peer")
+    px = shuffle.PeerExchange(cap, local) if transport == "peer" else None
+    d_out = None if px else torch.empty(cap, dtype=torch.uint8, device=dev)
+    step_no = [0]
     d_merged = torch.empty(int(cap * 1.3) + (1 << 20), dtype=torch.uint8, device=dev)
     p0, p1 = shuffle.owner_ranges(P, world)[rank]
     launches = [0]
     merger = [None]
     phase_ms = {"sort": [], "exchange": [], "merge": []}
+    fetch_ms = []
 
     def step(timed):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record()
-        out_len, index, st = sorter.sort_device_fixed(d_kv.data_ptr(), n, d_out.data_ptr(), cap)
+        k = step_no[0]
+        step_no[0] += 1
+        out_ptr = px.out_ptr(k) if px else d_out.data_ptr()
+        out_len, index, st = sorter.sort_device_fixed(d_kv.data_ptr(), n, out_ptr, cap)
         e[1].record()
-        recv, segs = shuffle.exchange_partitions(d_out[:out_len], index, P)
+        if px:
+            segs = px.exchange(k, index, P)   # returns once the pulled bytes have landed
+            seg_list = [(ptr, ln) for ptr, ln, _, _ in segs]
+            if timed:
+                fetch_ms.append(px.last_fetch_ms)
+        else:
+            recv, segs = shuffle.exchange_partitions(d_out[:out_len], index, P)
+            base = recv.data_ptr()
+            seg_list = [(base + off, ln) for off, ln, _, _ in segs]
         e[2].record()
         # the library works on its own stream: the received bytes must have landed before it reads them
         torch.cuda.current_stream().synchronize()
-        base = recv.data_ptr()
-        seg_list = [(base + off, ln) for off, ln, _, _ in segs]
         parts = [p for _, _, p, _ in segs]
         if merger[0] is None:
             merger[0] = T.GpuMerger(seg_list, comparator=T.CMP_BYTES, device=local, device_ptrs=True,
@@ -105,12 +121,19 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
                 "phases_ms_rank0": avg,
                 "nvlink": {"bytes_sent_per_gpu_per_step": sent,
                            "achieved_GBps_per_gpu": round(sent / (avg["exchange"] * 1e-3) / 1e9, 1) if avg["exchange"] else None,
-                           "reference_GBps": 770, "note": "variable-size all-to-all (NCCL send/recv) incl. index all-gather"},
+                           "fetch_kernel_ms": round(sum(fetch_ms) / len(fetch_ms), 3) if fetch_ms else None,
+                           "fetch_kernel_GBps_per_gpu": round(sent / (sum(fetch_ms) / len(fetch_ms) * 1e-3) / 1e9, 1) if fetch_ms and sum(fetch_ms) else None,
+                           "transport": transport, "reference_GBps": 770,
+                           "note": ("peer pull: index all-gather (NCCL) + one fetch kernel over CUDA IPC mappings; own partitions merged in place"
+                                    if px else "variable-size all-to-all (NCCL send/recv) incl. index all-gather")},
                 "roofline": {"bound": "hbm", "achieved": round(n * (2 * 162) / (ms_step * 1e-3) / 1e9, 1), "peak": peak,
                              "unit": "GB/s", "frac": round(n * (2 * 162) / (ms_step * 1e-3) / 1e9 / peak, 4),
                              "traffic": None, "peak_source": peak_src,
                              "note": "per GPU: sort (162 B/rec) + merge (164 B/rec) algorithmic bytes over the whole step"},
                 "cpu_baseline": None}
         print(json.dumps(line))
+    if px:
+        dist.barrier()
+        px.close()
     dist.destroy_process_group()
     return 0

@@ -214,3 +214,48 @@ class GpuMerger:
 
     def stream(self):
         return self.L.tezgpu_merge_stream(self.h)
+
+
+class PeerBuffer:
+    """Device buffer other processes of the box can map (tezgpu_peer_alloc): where a producer keeps file.out."""
+
+    def __init__(self, nbytes, device=0):
+        self.L = _lib.load()
+        self.device, self.nbytes = device, int(nbytes)
+        p = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        check(self.L.tezgpu_peer_alloc(device, self.nbytes, C.byref(p), handle))
+        self.ptr, self.handle = p.value, bytes(handle)
+
+    def close(self):
+        if self.ptr:
+            check(self.L.tezgpu_peer_free(self.device, self.ptr))
+            self.ptr = None
+
+
+class PeerMapping:
+    """A peer's exported buffer mapped into this process (tezgpu_peer_open)."""
+
+    def __init__(self, handle, device=0):
+        self.L = _lib.load()
+        self.device = device
+        p = C.c_void_p()
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        check(self.L.tezgpu_peer_open(device, buf, C.byref(p)))
+        self.ptr = p.value
+
+    def close(self):
+        if self.ptr:
+            check(self.L.tezgpu_peer_close(self.device, self.ptr))
+            self.ptr = None
+
+
+def fetch_ranges(ranges, device=0, stream=None):
+    """ranges: list of (src_ptr, dst_ptr, nbytes) device addresses; one launch, returns the kernel time in ms."""
+    L = _lib.load()
+    arr = (_lib.CopyRange * max(1, len(ranges)))()
+    for i, (s, d, n) in enumerate(ranges):
+        arr[i].src, arr[i].dst, arr[i].len = s, d, n
+    ms = C.c_float()
+    check(L.tezgpu_fetch_ranges(device, arr, len(ranges), stream, C.byref(ms)))
+    return ms.value

@@ -7,7 +7,10 @@ producer's file.out already stores its partitions in partition order, the bytes 
 contiguous range of file.out: the exchange is a single variable-size all-to-all (NCCL send/recv pairs over NVLink)
 with no repacking, preceded by an all-gather of the TezSpillRecord index (P x 3 int64 per rank).
 
-Pure torch.distributed plumbing: works on CUDA tensors over NCCL and on CPU tensors over gloo (tests).
+exchange_partitions() is pure torch.distributed plumbing: works on CUDA tensors over NCCL and on CPU tensors over
+gloo (tests).  PeerExchange is the fast path on an NVSwitch box: every producer keeps file.out in an exported device
+buffer, consumers map it once and pull their byte ranges with libtezgpu's fetch kernel (all SMs, 128-bit words);
+a rank's own partitions are merged in place, they never move.
 """
 import numpy as np
 import torch
@@ -51,3 +54,91 @@ def exchange_partitions(file_out, index, num_partitions, group=None):
                 segments.append((off, ln, p - p0, g))
             off += ln
     return recv, segments
+
+
+def _gather_index(index, group, device):
+    """all-gather of the [P,3] spill index -> [world, P, 3] numpy (device tensors over NCCL, CPU tensors over gloo)."""
+    world = dist.get_world_size(group)
+    on_dev = dist.get_backend(group) == "nccl"
+    idx = torch.from_numpy(np.ascontiguousarray(index, dtype=np.int64))
+    if on_dev:
+        idx = idx.to(device)
+    out = [torch.empty_like(idx) for _ in range(world)]
+    dist.all_gather(out, idx, group=group)
+    return torch.stack(out).cpu().numpy()
+
+
+class PeerExchange:
+    """NVLink pull shuffle.  Each rank owns `slots` exported file.out buffers used round-robin (step k writes slot
+    k % slots): with two slots the index all-gather of step k+1 is the only synchronisation needed -- a peer has
+    finished pulling step k's bytes before it enters that all-gather, and slot k % 2 is not rewritten before step k+2."""
+
+    def __init__(self, out_capacity, device, group=None, slots=2):
+        from . import native
+        self.group, self.device = group, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.slots = [native.PeerBuffer(out_capacity, device) for _ in range(slots)]
+        self.capacity = int(out_capacity)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, [b.handle for b in self.slots], group=group)
+        self.peers = []  # peers[g][slot] -> device address of rank g's slot in this process
+        self._maps = []
+        for g in range(self.world):
+            if g == self.rank:
+                self.peers.append([b.ptr for b in self.slots])
+            else:
+                maps = [native.PeerMapping(h, device) for h in handles[g]]
+                self._maps += maps
+                self.peers.append([m.ptr for m in maps])
+        self._recv = None
+        self.last_fetch_ms = 0.0
+
+    def out_ptr(self, step):
+        return self.slots[step % len(self.slots)].ptr
+
+    def exchange(self, step, index, num_partitions):
+        """index: this rank's [P,3] spill index of the file.out it just wrote into slot `step`.
+        Returns segments [(device_ptr, length, local_partition, source_rank)] ordered by (source_rank, partition):
+        own segments point into the local slot, the others into the receive buffer the pull kernel filled."""
+        from . import native
+        slot = step % len(self.slots)
+        all_idx = _gather_index(index, self.group, torch.device("cuda", self.device))
+        p0, p1 = owner_ranges(num_partitions, self.world)[self.rank]
+        ranges, seg_src = [], {}
+        need = 0
+        for g in range(self.world):
+            if g == self.rank or p1 <= p0:
+                continue
+            a = int(all_idx[g, p0, 0])
+            ln = int(all_idx[g, p0:p1, 2].sum())
+            src = self.peers[g][slot] + a
+            off = (need + 15) // 16 * 16 + (src & 15)   # same address modulo 16 on both sides: 128-bit moves
+            seg_src[g] = (off, a)
+            need = off + ln
+            if ln:
+                ranges.append((g, src, off, ln))
+        if self._recv is None or self._recv.numel() < need + 64:
+            self._recv = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, device=torch.device("cuda", self.device))
+        base = self._recv.data_ptr()
+        self.last_fetch_ms = native.fetch_ranges([(src, base + off, ln) for _, src, off, ln in ranges], self.device)
+        segments = []
+        for g in range(self.world):
+            for p in range(p0, p1):
+                ln = int(all_idx[g, p, 2])
+                if not ln:
+                    continue
+                start = int(all_idx[g, p, 0])
+                if g == self.rank:
+                    ptr = self.peers[g][slot] + start
+                else:
+                    off, a = seg_src[g]
+                    ptr = base + off + (start - a)
+                segments.append((ptr, ln, p - p0, g))
+        return segments
+
+    def close(self):
+        for m in self._maps:
+            m.close()
+        for b in self.slots:
+            b.close()
+        self._maps, self.slots = [], []
