@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtezgpu.so")
+# TEZGPU_LIB: developer override to A/B another build of the same library (tools/variants/)
+LIB_PATH = os.environ.get("TEZGPU_LIB") or os.path.join(HERE, "libtezgpu.so")
 
 
 class Conf(C.Structure):

@@ -17,10 +17,24 @@
 #ifndef TEZGPU_EMIT4_MIN_CTAS
 #define TEZGPU_EMIT4_MIN_CTAS 3
 #endif
+#ifndef TEZGPU_EMIT4_MAP16
+#define TEZGPU_EMIT4_MAP16 0
+#endif
 
 namespace tezgpu {
 
 constexpr int FE4_BATCH = FE_THREADS / 32;  // one parked tile per warp
+constexpr int FE4_UNROLL = TEZGPU_EMIT4_MAP16 ? 6 : 5;  // gather rounds held in registers
+
+// can a tile of `recs` records with `cpr` pieces each be gathered in FE4_UNROLL rounds?
+static inline bool emit4_fits(uint32_t recs, uint32_t cpr) {
+#if TEZGPU_EMIT4_MAP16
+  const uint32_t rph = 16u / cpr;
+  return cpr <= 8 && 16ull * ((recs + rph - 1) / rph) <= (uint64_t)FE4_UNROLL * FE_THREADS;
+#else
+  return (uint64_t)recs * cpr <= (uint64_t)FE4_UNROLL * FE_THREADS;
+#endif
+}
 
 struct FoldMeta {
   uint4 tail;       // the 16-byte chunk holding the bytes the chunk loop did not fold
@@ -36,54 +50,134 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
   return v;
 }
 
-template <int UNROLL>
-__global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast4(FastEmitParams fp) {
-  __shared__ __align__(16) uint8_t s_img[FE_IMG_BYTES];
-  __shared__ uint32_t s_idx[3][FE_MAX_RECS];  // record indices of tiles N, N+1, N+2 (round robin)
-  __shared__ uint32_t s_tab[256];             // classic byte table (trailing bytes)
-  __shared__ uint32_t s_adv128[4 * 256];      // * x^(32*128): second-level fold
-  __shared__ uint32_t s_part[FE4_BATCH][FE_THREADS];
-  __shared__ FoldMeta s_meta[FE4_BATCH];
+// SUBS = 1: one 256-thread group per CTA, TEZGPU_EMIT4_MIN_CTAS CTAs per SM, both checksum maps as SHFL digit tables.
+// SUBS = 3: one CTA per SM hosts three independent 256-thread groups (named barriers) that share a LANE-PRIVATE copy
+//           of the four "next word" byte tables (entry e of table k for lane l lives at word (k*256+e)*32+l, always
+//           bank l): the look-up that runs three times per chunk becomes 4 conflict-free LDS instead of 7 SHFL.
+//           Measured on the SHFL-only kernel: a SHFL occupies the LSU data pipe for two cycles, so its 28 SHFL per
+//           chunk cost as much pipe time as the conflicting byte-table look-ups they replaced; the pipe, not issue
+//           or DRAM, bounded the kernel.
+template <int SUBS>
+struct Emit4Smem {
+  static constexpr int BATCH = SUBS > 1 ? 4 : FE4_BATCH;
+  static constexpr size_t WTAB = SUBS > 1 ? (size_t)4 * 256 * 32 * 4 : 0;
+  static constexpr size_t SHARED = WTAB + 256 * 4 + 4 * 256 * 4;
+  static constexpr size_t GROUP = FE_IMG_BYTES + 3 * FE_MAX_RECS * 4 + (size_t)BATCH * FE_THREADS * 4 + (size_t)BATCH * sizeof(FoldMeta);
+  static constexpr size_t TOTAL = SHARED + SUBS * GROUP;
+};
+
+template <int UNROLL, int SUBS>
+__global__ void __launch_bounds__(FE_THREADS * SUBS, SUBS > 1 ? 1 : TEZGPU_EMIT4_MIN_CTAS) k_emit_fast4(FastEmitParams fp) {
+  using L = Emit4Smem<SUBS>;
+  constexpr int BATCH = L::BATCH;
+  extern __shared__ __align__(16) uint8_t smem4[];
+  uint32_t *s_wtab = reinterpret_cast<uint32_t *>(smem4);              // [4][256][32] lane-private (SUBS > 1)
+  uint32_t *s_tab = reinterpret_cast<uint32_t *>(smem4 + L::WTAB);     // classic byte table (trailing bytes)
+  uint32_t *s_adv128 = s_tab + 256;                                    // * x^(32*128): second-level fold
+  const int sub = threadIdx.x / FE_THREADS, tid = threadIdx.x % FE_THREADS, lane = tid & 31, warp = tid >> 5;
+  uint8_t *gbase = smem4 + L::SHARED + (size_t)sub * L::GROUP;
+  uint8_t *s_img = gbase;
+  uint32_t(*s_idx)[FE_MAX_RECS] = reinterpret_cast<uint32_t(*)[FE_MAX_RECS]>(gbase + FE_IMG_BYTES);  // tiles N, N+1, N+2
+  uint32_t(*s_part)[FE_THREADS] = reinterpret_cast<uint32_t(*)[FE_THREADS]>(gbase + FE_IMG_BYTES + 3 * FE_MAX_RECS * 4);
+  FoldMeta *s_meta = reinterpret_cast<FoldMeta *>(gbase + FE_IMG_BYTES + 3 * FE_MAX_RECS * 4 + (size_t)BATCH * FE_THREADS * 4);
+  auto group_sync = [&]() {
+    if (SUBS == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(sub + 1), "r"(FE_THREADS) : "memory");
+  };
 
   const EmitParams &e = fp.e;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t G = gridDim.x, ntiles = fp.ntiles;
-  uint32_t tile = blockIdx.x;
+  const uint32_t G = gridDim.x * SUBS, ntiles = fp.ntiles;
+  uint32_t tile = blockIdx.x * SUBS + sub;
+  if (SUBS > 1)
+    for (int i = threadIdx.x; i < 4 * 256 * 32; i += FE_THREADS * SUBS) s_wtab[i] = (&e.crc->slice[0][0])[i >> 5];
+  for (int i = threadIdx.x; i < 256; i += FE_THREADS * SUBS) s_tab[i] = e.crc->slice[0][i];
+  for (int i = threadIdx.x; i < 4 * 256; i += FE_THREADS * SUBS) s_adv128[i] = (&e.crc->adv128[0][0])[i];
+  __syncthreads();
   if (tile >= ntiles) return;
-  s_tab[tid] = e.crc->slice[0][tid];
-  for (int i = tid; i < 4 * 256; i += FE_THREADS) s_adv128[i] = (&e.crc->adv128[0][0])[i];
   const uint32_t lane_pow = e.crc->pow_word[4 * (31 - lane)];
   WarpLinearMap m_word, m_skip;  // "* x^32" and "* x^(32*(4*FE_THREADS-3))" as warp-resident digit tables
   {
     const uint32_t *gt = &e.crc->slice[0][0], *ga = &e.crc->advc[0][0];
-    m_word.init([&](uint32_t x) { return gt[768 + (x & 0xFF)] ^ gt[512 + ((x >> 8) & 0xFF)] ^ gt[256 + ((x >> 16) & 0xFF)] ^ gt[x >> 24]; }, lane);
+    if (SUBS == 1)
+      m_word.init([&](uint32_t x) { return gt[768 + (x & 0xFF)] ^ gt[512 + ((x >> 8) & 0xFF)] ^ gt[256 + ((x >> 16) & 0xFF)] ^ gt[x >> 24]; }, lane);
     m_skip.init([&](uint32_t x) { return ga[x & 0xFF] ^ ga[256 + ((x >> 8) & 0xFF)] ^ ga[512 + ((x >> 16) & 0xFF)] ^ ga[768 + (x >> 24)]; }, lane);
   }
+  const uint32_t *wt = s_wtab + lane;  // this lane's bank
+  auto next_word = [&](uint32_t x) -> uint32_t {
+    if (SUBS == 1) return m_word.apply(x);
+    return wt[(768u + (x & 0xFFu)) << 5] ^ wt[(512u + ((x >> 8) & 0xFFu)) << 5] ^ wt[(256u + ((x >> 16) & 0xFFu)) << 5] ^ wt[(x >> 24) << 5];
+  };
   const uint32_t img_base = (uint32_t)__cvta_generic_to_shared(s_img);
   const uint8_t *__restrict__ kv = e.rec.kv;
   const uint32_t rec_size = e.rec_size, hdr_len = e.fixed_hdr_len, stride = fp.stride, cpr = fp.cpr;
   const TileDesc *__restrict__ tiles = fp.tiles;
 
-  // piece q of a tile <-> (record j, 16-byte piece c): even records first, then odd ones (emit_fast.cuh)
-  auto piece = [&](uint32_t q, uint32_t nr, uint32_t &j, uint32_t &c) {
+  // piece slot of a tile <-> (record j, 16-byte piece c).
+  // MAP16 = 0: consecutive lanes take consecutive pieces, records straddle the 8-lane quarters a 128-bit warp load is
+  //            split into, so a quarter touches the lines of up to three records;
+  // MAP16 = 1: every half-warp takes 16/cpr whole records (leftover lanes idle): fewer distinct 128-byte lines per
+  //            quarter -> fewer L1 wavefronts for the random gather.
+  // Even records first, then odd ones (emit_fast.cuh): keeps a warp on one unaligned-store path.
+#if TEZGPU_EMIT4_MAP16
+  const uint32_t rph = 16u / cpr;                       // records per half-warp
+  const uint32_t hl = tid & 15u, rl = hl / cpr, pc = hl - rl * cpr;
+  const bool lane_used = rl < rph;
+  auto piece = [&](int u, uint32_t nr, uint32_t &j, uint32_t &c) -> bool {
+    const uint32_t jp = (((uint32_t)tid >> 4) + 16u * (uint32_t)u) * rph + rl;
+    c = pc;
+    const uint32_t half_up = (nr + 1) >> 1;
+    j = jp < half_up ? 2u * jp : 2u * (jp - half_up) + 1u;
+    return lane_used && jp < nr;
+  };
+#else
+  auto piece = [&](int u, uint32_t nr, uint32_t &j, uint32_t &c) -> bool {
+    const uint32_t q = tid + u * FE_THREADS;
     const uint32_t jp = cpr == 1 ? q : __umulhi(q, fp.cpr_magic);
     c = q - jp * cpr;
     const uint32_t half_up = (nr + 1) >> 1;
     j = jp < half_up ? 2u * jp : 2u * (jp - half_up) + 1u;
+    return q < nr * cpr;
   };
-  uint4 v[UNROLL];
-  auto issue_gather = [&](uint32_t nr, const uint32_t *idx) {
-    const uint32_t npieces = nr * cpr;
+#endif
+  // Full tiles (all but the last of a partition) share one piece map: packed once per thread as
+  // j | 16c << 8 | (j * rec_size + hdr_len + 16c) << 15, so a piece costs an index look-up and one multiply-add
+  // instead of the divide / permute arithmetic (which was ~25 % of the kernel's instructions).
+  const uint32_t full_nr = e.recs_per_tile;
+  uint32_t pk[UNROLL], onmask = 0;
 #pragma unroll
-    for (int u = 0; u < UNROLL; u++) {
-      const uint32_t q = tid + u * FE_THREADS;
-      if (q < npieces) {
+  for (int u = 0; u < UNROLL; u++) {
+    uint32_t j, c;
+    const bool on = piece(u, full_nr, j, c);
+    pk[u] = on ? (j | (16u * c) << 8 | (j * rec_size + hdr_len + 16u * c) << 15) : 0u;
+    onmask |= on ? 1u << u : 0u;
+  }
+  uint4 v[UNROLL];
+  // all addresses first, then the loads back to back (keeps ptxas from reusing the destination registers of later
+  // rounds as temporaries between the loads)
+  auto issue_gather = [&](uint32_t nr, const uint32_t *idx) {
+    const uint8_t *src[UNROLL];
+    bool on[UNROLL];
+    if (nr == full_nr) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        on[u] = (onmask >> u) & 1u;
+        src[u] = kv + (uint64_t)idx[pk[u] & 0xFFu] * stride + ((pk[u] >> 8) & 0x7Fu);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
         uint32_t j, c;
-        piece(q, nr, j, c);
-        v[u] = ldg_stream_v4(kv + (uint64_t)idx[j] * stride + 16u * c);
+        on[u] = piece(u, nr, j, c);
+        src[u] = kv + (uint64_t)idx[on[u] ? j : 0u] * stride + 16u * c;
       }
     }
+    if (UNROLL == 5) asm volatile("" : "+l"(src[0]), "+l"(src[1]), "+l"(src[2]), "+l"(src[3]), "+l"(src[UNROLL - 1]));
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++)
+      if (on[u]) v[u] = ldg_stream_v4(src[u]);
   };
+  // vint(klen) vint(vlen) of the fixed framing as one 16-bit store when it is two bytes at an even address
+  const uint32_t hdr16 = (uint32_t)e.fixed_hdr[0] | (uint32_t)e.fixed_hdr[1] << 8;
 
   // ---- prologue: descriptors of tiles 0..2 of this CTA, indices of tiles 0 and 1, gather of tile 0 in flight
   uint32_t nr0, fl0, nr1 = 0, fl1 = 0, r0_2 = 0, nr2 = 0;
@@ -99,7 +193,7 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast
     }
     if (tile + 2 * (uint64_t)G < ntiles) { r0_2 = tiles[tile + 2 * G].r0; nr2 = tiles[tile + 2 * G].nr; }
   }
-  __syncthreads();
+  group_sync();
   issue_gather(nr0, s_idx[0]);
 
   uint32_t n_it = 0, slot = 0;
@@ -122,27 +216,27 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast
     if (has3) { const TileDesc *t3 = tiles + tile + 3 * (uint64_t)G; r0_3 = t3->r0; nr3 = t3->nr; }
 
     // ---- this tile's pieces (loaded during the previous iteration) -> image; framing
-    {
-      const uint32_t npieces = nr * cpr;
+    if (nr == full_nr) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++)
+        if ((onmask >> u) & 1u) sts16_unaligned(img_base + rec0 + (pk[u] >> 15), v[u]);
+    } else {
 #pragma unroll
       for (int u = 0; u < UNROLL; u++) {
-        const uint32_t q = tid + u * FE_THREADS;
-        if (q < npieces) {
-          uint32_t j, c;
-          piece(q, nr, j, c);
-          sts16_unaligned(img_base + rec0 + j * rec_size + hdr_len + 16u * c, v[u]);
-        }
+        uint32_t j, c;
+        if (piece(u, nr, j, c)) sts16_unaligned(img_base + rec0 + j * rec_size + hdr_len + 16u * c, v[u]);
       }
     }
     if ((uint32_t)tid < nr) {
       const uint32_t a = img_base + rec0 + tid * rec_size;
-      for (uint32_t b = 0; b < hdr_len; b++) sts_b8(a + b, e.fixed_hdr[b]);
+      if (hdr_len == 2 && !(a & 1u)) sts_b16(a, hdr16);
+      else for (uint32_t b = 0; b < hdr_len; b++) sts_b8(a + b, e.fixed_hdr[b]);
     }
     if (tid == 0) {
       if (first_tile) { s_img[lead] = 'T'; s_img[lead + 1] = 'I'; s_img[lead + 2] = 'F'; s_img[lead + 3] = 0; }
       if (last_tile) { s_img[body_end - 2] = 0xFF; s_img[body_end - 1] = 0xFF; }
     }
-    __syncthreads();  // (B) image complete
+    group_sync();  // (B) image complete
 
     // ---- gather of the next tile goes out now; it lands while this tile is checksummed and written
     if (has1) issue_gather(nr1, s_idx[(n_it + 1) % 3]);
@@ -159,6 +253,7 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast
       uint32_t sa = img_base + 16u * (uint32_t)((int32_t)ca + i);
       uint8_t *gp = dstg + 16ll * ((int64_t)ca + i);
       for (uint32_t it = 0; it < iters; it++, i += FE_THREADS, sa += 16u * FE_THREADS, gp += 16 * FE_THREADS) {
+        if (i + (31 - lane) < 0) continue;  // no lane of this warp owns a chunk yet (first, ragged round only)
         uint4 w = make_uint4(0, 0, 0, 0);
         if (i >= 0) {
           w = lds_v4(sa);
@@ -180,10 +275,10 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast
             stg_stream_v4(gp, w);
           }
         }
-        uint32_t x = m_word.apply(c ^ w.x) ^ w.y;
-        x = m_word.apply(x) ^ w.z;
-        x = m_word.apply(x) ^ w.w;
-        c = (it + 1 == iters) ? m_word.apply(x) : m_skip.apply(x);
+        uint32_t x = next_word(c ^ w.x) ^ w.y;
+        x = next_word(x) ^ w.z;
+        x = next_word(x) ^ w.w;
+        c = (it + 1 == iters) ? next_word(x) : m_skip.apply(x);
       }
     }
     s_part[slot][tid] = c;
@@ -201,9 +296,9 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast
     }
     if (has2) s_idx[(n_it + 2) % 3][tid] = r_idx;
     slot++;
-    __syncthreads();  // (C) image free, partials / indices visible
+    group_sync();  // (C) image free, partials / indices visible
 
-    if (slot == FE4_BATCH || !has1) {
+    if (slot == (uint32_t)BATCH || !has1) {
       // ---- deferred second level: warp w folds parked tile w.  lane l folds partials l, l+32, ... (Horner with
       // x^(128*32)), aligns by x^(128*(31-l)), xor-reduce; lane 0 appends the trailing bytes
       if ((uint32_t)warp < slot) {
@@ -236,6 +331,10 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast
       // the parked rows are rewritten only after barrier (B) of the next iteration, which every folding warp joins
     }
     if (!has1) break;
+    // the descriptor prefetches are consumed HERE: without this the compiler renames them straight into the next
+    // iteration, where their scoreboard is shared with the freshly issued gather loads and the first use stalls on
+    // those (measured: 20 % of all warp samples on one integer add in the middle of the gather)
+    asm volatile("" : "+r"(nr2n), "+r"(fl2n), "+l"(abs2n), "+r"(r0_3), "+r"(nr3));
     nr0 = nr1; fl0 = fl1; abs0 = abs1;
     nr1 = nr2n; fl1 = fl2n; abs1 = abs2n;
     r0_2 = r0_3; nr2 = nr3;

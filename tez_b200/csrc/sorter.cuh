@@ -417,11 +417,31 @@ class SortPipeline {
           }
           uint32_t grid = (uint32_t)std::min<uint64_t>(div_up(tiles, FE3_SUBS), (uint64_t)num_sms);
           k_emit_fast3<5><<<grid, FE3_THREADS, FE3_SMEM, stream>>>(fp);
-        } else if (fast_aligned && (uint64_t)e.recs_per_tile * fp.cpr <= 5u * FE_THREADS && !getenv("TEZGPU_EMIT_V2")) {
-          // software-pipelined kernel (emit_pipe.cuh): a tile's pieces must fit the registers of one gather round
-          TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_fast4<5>, FE_THREADS, 0));
-          uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));
-          k_emit_fast4<5><<<grid, FE_THREADS, 0, stream>>>(fp);
+        } else if (fast_aligned && emit4_fits(e.recs_per_tile, fp.cpr) && !getenv("TEZGPU_EMIT_V2")) {
+          // software-pipelined kernel (emit_pipe.cuh): a tile's pieces must fit the registers of one gather round.
+          // Default: independent 256-thread CTAs, three per SM.  TEZGPU_EMIT_SUBS=3 selects the variant with one CTA
+          // per SM whose three groups share lane-private checksum tables -- measured SLOWER (8.39 vs 5.44 ms): its
+          // 219 KB of shared memory leave the SM ~30 KB of L1 and the random gather loses its memory-level parallelism.
+          static const bool subs1 = !(getenv("TEZGPU_EMIT_SUBS") && atoi(getenv("TEZGPU_EMIT_SUBS")) == 3);
+          if (!subs1) {
+            constexpr int SUBS = 3;
+            static bool attr = false;
+            if (!attr) {
+              TG_CUDA(cudaFuncSetAttribute(k_emit_fast4<FE4_UNROLL, SUBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Emit4Smem<SUBS>::TOTAL));
+              attr = true;
+            }
+            uint32_t grid = (uint32_t)std::min<uint64_t>(div_up(tiles, SUBS), (uint64_t)num_sms);
+            k_emit_fast4<FE4_UNROLL, SUBS><<<grid, FE_THREADS * SUBS, Emit4Smem<SUBS>::TOTAL, stream>>>(fp);
+          } else {
+            static bool attr = false;
+            if (!attr) {
+              TG_CUDA(cudaFuncSetAttribute(k_emit_fast4<FE4_UNROLL, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Emit4Smem<1>::TOTAL));
+              attr = true;
+            }
+            TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_fast4<FE4_UNROLL, 1>, FE_THREADS, Emit4Smem<1>::TOTAL));
+            uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));
+            k_emit_fast4<FE4_UNROLL, 1><<<grid, FE_THREADS, Emit4Smem<1>::TOTAL, stream>>>(fp);
+          }
         } else if (fast_aligned) {
           TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_fast<5, true>, FE_THREADS, 0));
           uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));
