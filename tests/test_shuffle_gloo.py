@@ -65,3 +65,45 @@ def test_partition_exchange_world2(P):
     assert shuffle.owner_ranges(8, 2) == [(0, 4), (4, 8)]
     assert shuffle.owner_ranges(5, 2) == [(0, 3), (3, 5)]
     assert shuffle.owner_ranges(1024, 8)[3] == (384, 512)
+
+
+def test_pull_plan_and_segment_table_resolve_to_the_right_bytes():
+    """The NVLink pull shuffle's planning (pure numpy): emulate device memory with fake address spaces and check that
+    every segment address resolves to the producer's bytes, in (source rank, partition) order, for every rank."""
+    import numpy as np
+    from tez_b200 import shuffle
+    rng = np.random.default_rng(7)
+    world, P = 4, 13
+    files, indexes = [], []
+    for g in range(world):
+        lens = rng.integers(0, 200, size=P)
+        lens[rng.integers(0, P)] = 0                     # an empty partition
+        idx = np.zeros((P, 3), dtype=np.int64)
+        idx[:, 0] = np.concatenate([[0], np.cumsum(lens)[:-1]]) + 3   # file.out ranges (arbitrary start)
+        idx[:, 1] = np.maximum(lens - 4, 0)
+        idx[:, 2] = lens
+        files.append(rng.integers(0, 256, size=int(lens.sum()) + 3, dtype=np.uint8))
+        indexes.append(idx)
+    all_idx = np.stack(indexes)
+    peer_ptrs = [(g + 1) << 40 | (5 * g + 1) for g in range(world)]     # deliberately unaligned file.out addresses
+    recv_base = 1 << 50
+    for rank in range(world):
+        ranges, seg_src, need = shuffle.pull_plan(all_idx, rank, P, peer_ptrs)
+        assert [g for g, _, _, _ in ranges] == [(rank + k) % world for k in range(1, world) if any(r[0] == (rank + k) % world for r in ranges)]
+        recv = np.zeros(need + 16, dtype=np.uint8)
+        for g, src, off, ln in ranges:
+            assert (src - (recv_base + off)) % 16 == 0           # 128-bit moves possible
+            a = src - peer_ptrs[g]
+            recv[off:off + ln] = files[g][a:a + ln]              # what the fetch kernel does
+        segs = shuffle.pull_segments(all_idx, rank, P, peer_ptrs, seg_src, recv_base)
+        p0, p1 = shuffle.owner_ranges(P, world)[rank]
+        want = [(g, p) for g in range(world) for p in range(p0, p1) if indexes[g][p, 2]]
+        assert [(g, p0 + lp) for _, _, lp, g in segs] == want
+        for ptr, ln, lp, g in segs:
+            s0, l0 = int(indexes[g][p0 + lp, 0]), int(indexes[g][p0 + lp, 2])
+            assert ln == l0
+            if g == rank:
+                got = files[g][ptr - peer_ptrs[g]: ptr - peer_ptrs[g] + ln]
+            else:
+                got = recv[ptr - recv_base: ptr - recv_base + ln]
+            assert np.array_equal(got, files[g][s0:s0 + l0])

@@ -22,8 +22,7 @@ constexpr uint64_t FETCH_CHUNK = (uint64_t)FETCH_THREADS * FETCH_UNROLL * 16 * 2
 // the producer rewrites its buffer every step: never serve a peer byte from a local cache line (ld.cv)
 __device__ __forceinline__ uint4 ld_peer_16(const uint4 *p) { return __ldcv(p); }
 
-__global__ void __launch_bounds__(FETCH_THREADS)
-    k_fetch_ranges(const FetchRange *__restrict__ ranges, uint32_t nranges, uint64_t nchunks) {
+__device__ __forceinline__ void fetch_ranges_body(const FetchRange *__restrict__ ranges, uint32_t nranges, uint64_t nchunks) {
   for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
     uint32_t lo = 0, hi = nranges;  // last range with chunk0 <= c
     while (hi - lo > 1) {
@@ -60,6 +59,19 @@ __global__ void __launch_bounds__(FETCH_THREADS)
         r.dst[tail0 + (threadIdx.x - 32)] = r.src[tail0 + (threadIdx.x - 32)];
     }
   }
+}
+
+__global__ void __launch_bounds__(FETCH_THREADS)
+    k_fetch_ranges(const FetchRange *__restrict__ ranges, uint32_t nranges, uint64_t nchunks) {
+  fetch_ranges_body(ranges, nranges, nchunks);
+}
+
+// the usual case -- one range per peer GPU -- needs no device-side table: the ranges ride in the parameter space
+constexpr uint32_t FETCH_INLINE_RANGES = 16;
+struct FetchRangeList { FetchRange r[FETCH_INLINE_RANGES]; };
+__global__ void __launch_bounds__(FETCH_THREADS)
+    k_fetch_ranges_inline(const __grid_constant__ FetchRangeList lst, uint32_t nranges, uint64_t nchunks) {
+  fetch_ranges_body(lst.r, nranges, nchunks);
 }
 
 // number of chunks a range of `len` bytes starting at `src` occupies (at least one, so head/tail bytes always move)

@@ -374,10 +374,14 @@ int32_t tezgpu_fetch_ranges(int32_t device, const tezgpu_copy_range *ranges, uin
     chunks += fetch_chunks(ranges[i].src, ranges[i].dst, ranges[i].len);
   }
   if (chunks == 0) return TEZGPU_OK;
+  // ranges travel as a kernel parameter when they are few (one per peer GPU); larger lists through a device copy
   FetchRange *d_fr = nullptr;
-  TG_CUDA(cudaMalloc(&d_fr, (size_t)n * sizeof(FetchRange)));
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  cudaError_t err = cudaMemcpyAsync(d_fr, fr.data(), (size_t)n * sizeof(FetchRange), cudaMemcpyHostToDevice, st);
+  cudaError_t err = cudaSuccess;
+  if (n > FETCH_INLINE_RANGES) {
+    TG_CUDA(cudaMalloc(&d_fr, (size_t)n * sizeof(FetchRange)));
+    err = cudaMemcpyAsync(d_fr, fr.data(), (size_t)n * sizeof(FetchRange), cudaMemcpyHostToDevice, st);
+  }
   if (err == cudaSuccess && ms_kernel) {
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -387,7 +391,13 @@ int32_t tezgpu_fetch_ranges(int32_t device, const tezgpu_copy_range *ranges, uin
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const uint32_t grid = (uint32_t)std::min<uint64_t>(chunks, (uint64_t)sms * 2);
-    k_fetch_ranges<<<grid, FETCH_THREADS, 0, st>>>(d_fr, n, chunks);
+    if (d_fr) {
+      k_fetch_ranges<<<grid, FETCH_THREADS, 0, st>>>(d_fr, n, chunks);
+    } else {
+      FetchRangeList lst;
+      for (uint32_t i = 0; i < n; i++) lst.r[i] = fr[i];
+      k_fetch_ranges_inline<<<grid, FETCH_THREADS, 0, st>>>(lst, n, chunks);
+    }
     err = cudaGetLastError();
   }
   if (err == cudaSuccess && ms_kernel) cudaEventRecord(e1, st);
@@ -395,7 +405,7 @@ int32_t tezgpu_fetch_ranges(int32_t device, const tezgpu_copy_range *ranges, uin
   if (err == cudaSuccess && ms_kernel) cudaEventElapsedTime(ms_kernel, e0, e1);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
-  cudaFree(d_fr);
+  if (d_fr) cudaFree(d_fr);
   TG_CUDA(err);
   TG_API_END
 }

@@ -105,6 +105,11 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
     tot = torch.tensor([float(nrec), float(launches[0])], device=dev, dtype=torch.float64)
     dist.all_reduce(tot)
     ms_step = float(ms.item())
+    ph = torch.tensor([sum(phase_ms[k]) / max(1, len(phase_ms[k])) for k in ("sort", "exchange", "merge")] +
+                      [sum(fetch_ms) / max(1, len(fetch_ms))], device=dev, dtype=torch.float64)
+    ph_max, ph_min = ph.clone(), ph.clone()
+    dist.all_reduce(ph_max, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ph_min, op=dist.ReduceOp.MIN)
     clk = clocks.stop() if rank == 0 else None
     if rank == 0:
         total_records = n * world
@@ -119,6 +124,8 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
                 "config": workload_config(world, n), "clocks": clk, "gpu_launches": int(tot[1].item()),
                 "e2e": None,
                 "phases_ms_rank0": avg,
+                "phases_ms_over_ranks": {k: [round(float(ph_min[i]), 3), round(float(ph_max[i]), 3)]
+                                         for i, k in enumerate(("sort", "exchange", "merge", "fetch_kernel"))},
                 "nvlink": {"bytes_sent_per_gpu_per_step": sent,
                            "achieved_GBps_per_gpu": round(sent / (avg["exchange"] * 1e-3) / 1e9, 1) if avg["exchange"] else None,
                            "fetch_kernel_ms": round(sum(fetch_ms) / len(fetch_ms), 3) if fetch_ms else None,

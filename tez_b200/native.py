@@ -131,6 +131,15 @@ class GpuMerger:
         self._keep = []
         arr = (Segment * max(1, len(segments)))()
         flags = (SEG_HAS_HEADER if self._has_header else 0) | (SEG_DEVICE if self._device_ptrs else 0)
+        if self._device_ptrs and len(segments) > 64:
+            # many device-resident runs (the reduce side of the multi-GPU shuffle): fill the table through numpy
+            tab = np.zeros(len(segments), dtype=np.dtype([("data", "<u8"), ("len", "<u8"), ("flags", "<u4"), ("partition", "<u4")]))
+            sp = np.asarray(segments, dtype=np.uint64).reshape(-1, 2)
+            tab["data"], tab["len"], tab["flags"] = sp[:, 0], sp[:, 1], flags
+            if partitions is not None:
+                tab["partition"] = np.asarray(partitions, dtype=np.uint32)
+            self._keep.append(tab)
+            return C.cast(tab.ctypes.data, C.POINTER(Segment))
         for i, s in enumerate(segments):
             if self._device_ptrs:
                 arr[i].data, arr[i].len = s

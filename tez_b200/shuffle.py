@@ -68,6 +68,51 @@ def _gather_index(index, group, device):
     return torch.stack(out).cpu().numpy()
 
 
+def pull_plan(all_idx, rank, num_partitions, peer_ptrs):
+    """What rank `rank` pulls: all_idx is the gathered [world, P, 3] spill index, peer_ptrs[g] the address of rank g's
+    file.out in this process.  Returns (ranges, seg_src, need): ranges = [(g, src_address, offset_in_receive_buffer,
+    nbytes)], one per producer, in ring order starting at rank+1 (the classic all-to-all schedule: at any moment every
+    producer's HBM / NVLink egress serves one consumer instead of all consumers pulling from rank 0 first -- measured
+    at 4 GPUs with the naive order: the fetch kernel took 9.1 ms on one rank and 19.7 ms on another);
+    seg_src[g] = (receive offset, file offset) of g's range; need = receive buffer bytes.  Receive offsets agree
+    with the source address modulo 16 so the copy moves 128-bit words (the receive buffer is 16-byte aligned)."""
+    world = all_idx.shape[0]
+    p0, p1 = owner_ranges(num_partitions, world)[rank]
+    ranges, seg_src, need = [], {}, 0
+    for step_g in range(1, world):
+        g = (rank + step_g) % world
+        if p1 <= p0:
+            continue
+        a = int(all_idx[g, p0, 0])
+        ln = int(all_idx[g, p0:p1, 2].sum())
+        src = peer_ptrs[g] + a
+        off = (need + 15) // 16 * 16 + (src & 15)
+        seg_src[g] = (off, a)
+        need = off + ln
+        if ln:
+            ranges.append((g, src, off, ln))
+    return ranges, seg_src, need
+
+
+def pull_segments(all_idx, rank, num_partitions, peer_ptrs, seg_src, recv_base):
+    """Segment table after the pull: [(address, length, local_partition, source_rank)] ordered by (source_rank,
+    partition) -- the order TezMerger breaks ties in.  Own runs stay where the sorter wrote them."""
+    world = all_idx.shape[0]
+    p0, p1 = owner_ranges(num_partitions, world)[rank]
+    starts = all_idx[:, p0:p1, 0]
+    lens = all_idx[:, p0:p1, 2]
+    bases = np.zeros((world, 1), dtype=np.int64)
+    for g in range(world):
+        if g == rank:
+            bases[g, 0] = peer_ptrs[g]
+        elif g in seg_src:
+            off, a = seg_src[g]
+            bases[g, 0] = recv_base + off - a
+    ptrs = starts + bases
+    gs, ps = np.nonzero(lens)                          # row-major: ordered by (source_rank, partition)
+    return list(zip(ptrs[gs, ps].tolist(), lens[gs, ps].tolist(), ps.tolist(), gs.tolist()))
+
+
 class PeerExchange:
     """NVLink pull shuffle.  Each rank owns `slots` exported file.out buffers used round-robin (step k writes slot
     k % slots): with two slots the index all-gather of step k+1 is the only synchronisation needed -- a peer has
@@ -103,38 +148,13 @@ class PeerExchange:
         from . import native
         slot = step % len(self.slots)
         all_idx = _gather_index(index, self.group, torch.device("cuda", self.device))
-        p0, p1 = owner_ranges(num_partitions, self.world)[self.rank]
-        ranges, seg_src = [], {}
-        need = 0
-        for g in range(self.world):
-            if g == self.rank or p1 <= p0:
-                continue
-            a = int(all_idx[g, p0, 0])
-            ln = int(all_idx[g, p0:p1, 2].sum())
-            src = self.peers[g][slot] + a
-            off = (need + 15) // 16 * 16 + (src & 15)   # same address modulo 16 on both sides: 128-bit moves
-            seg_src[g] = (off, a)
-            need = off + ln
-            if ln:
-                ranges.append((g, src, off, ln))
+        peer_ptrs = [self.peers[g][slot] for g in range(self.world)]
+        ranges, seg_src, need = pull_plan(all_idx, self.rank, num_partitions, peer_ptrs)
         if self._recv is None or self._recv.numel() < need + 64:
             self._recv = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, device=torch.device("cuda", self.device))
         base = self._recv.data_ptr()
         self.last_fetch_ms = native.fetch_ranges([(src, base + off, ln) for _, src, off, ln in ranges], self.device)
-        segments = []
-        for g in range(self.world):
-            for p in range(p0, p1):
-                ln = int(all_idx[g, p, 2])
-                if not ln:
-                    continue
-                start = int(all_idx[g, p, 0])
-                if g == self.rank:
-                    ptr = self.peers[g][slot] + start
-                else:
-                    off, a = seg_src[g]
-                    ptr = base + off + (start - a)
-                segments.append((ptr, ln, p - p0, g))
-        return segments
+        return pull_segments(all_idx, self.rank, num_partitions, peer_ptrs, seg_src, base)
 
     def close(self):
         for m in self._maps:
