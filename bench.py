@@ -211,7 +211,7 @@ def single_gpu(args):
     emit = sum(emit_ms) / len(emit_ms)
     achieved = n * ALGO_BYTES_PER_RECORD / (emit * 1e-3) / 1e9
     traffic = load_traffic()
-    roofline = {"bound": "hbm", "kernel": "k_emit_fast<5,true> (gather + IFile framing + CRC32 + coalesced store)",
+    roofline = {"bound": "hbm", "kernel": "k_emit_fast4<5,1> (software-pipelined gather + IFile framing + CRC32 + coalesced store)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": n * ALGO_BYTES_PER_RECORD, "ms_per_launch": round(emit, 4)}
