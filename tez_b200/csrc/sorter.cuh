@@ -8,6 +8,9 @@
 
 #include "../../include/tezgpu.h"
 #include "device_util.h"
+#ifndef TEZGPU_EMIT_ROUND_FILL_DEFAULT
+#define TEZGPU_EMIT_ROUND_FILL_DEFAULT 0
+#endif
 #include "emit_pipe.cuh"
 #include "sorter_kernels.cuh"
 
@@ -136,6 +139,22 @@ class SortPipeline {
     e.rec_size = h + rec.klen + rec.vlen;
     // the tile image must fit the smallest image buffer of the emit kernels (k_emit_fast3: FE3_IMG bytes)
     e.recs_per_tile = std::max<uint32_t>(1, std::min<uint32_t>(EMIT_MAX_RECS, (FE3_IMG - 32) / e.rec_size));
+    // Round filling: the checksum / write-out loop of the source-oriented kernels walks a tile in rounds of
+    // FE_THREADS 16-byte chunks; 256 records of 82 bytes are 5.13 rounds, six are executed.  Among the tile sizes
+    // within 10 % of the cap, take the one with the most records per executed round (249 for 82-byte records).
+    static const int round_fill = getenv("TEZGPU_EMIT_ROUND_FILL") ? atoi(getenv("TEZGPU_EMIT_ROUND_FILL")) : TEZGPU_EMIT_ROUND_FILL_DEFAULT;
+    if (round_fill && e.recs_per_tile >= 32) {
+      const uint32_t cap = e.recs_per_tile;
+      uint32_t best = cap;
+      double best_eff = 0;
+      for (uint32_t r = cap; r >= cap - cap / 10; r--) {
+        const uint64_t chunks = ((uint64_t)r * e.rec_size + 15 + 4 + 2 + 15) / 16;  // worst-case lead, header, EOF
+        const uint64_t rounds = (chunks + FE_THREADS - 1) / FE_THREADS;
+        const double eff = (double)r / (double)rounds;
+        if (eff > best_eff) { best_eff = eff; best = r; }
+      }
+      e.recs_per_tile = best;
+    }
     e.rec_off = nullptr;
   }
 
