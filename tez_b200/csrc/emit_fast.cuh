@@ -372,173 +372,4 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT_MIN_CTAS) k_emit_fast(
 }
 
 
-// ------------------------------------------------------------------------------------------------------------------
-// k_emit_fast3: same tile algorithm as k_emit_fast<.,true>, restructured around the measured limiter (profiles/:
-// LSU data pipe 82 %, 58 % of the shared-load wavefronts were bank conflicts of the CRC table look-ups).  The four
-// slice-by-4 tables are stored lane-private -- entry e of table k for lane l at word (k*256+e)*32+l, i.e. ALWAYS in
-// bank l -- so those look-ups (12 of 16 per 16-byte chunk) are conflict free.  That costs 128 KiB of shared memory,
-// so ONE CTA per SM hosts three independent 256-thread groups ("sub-CTAs", named barriers 1..3) that share the tables
-// and each run the tile loop on their own 21.5 KiB image.
-constexpr int FE3_SUBS = 3;
-constexpr int FE3_THREADS = FE3_SUBS * FE_THREADS;
-constexpr int FE3_IMG = 22016;  // 256 records * 82 B + lead + header + EOF, multiple of 16
-constexpr size_t FE3_SMEM = (size_t)4 * 256 * 32 * 4 + (size_t)FE3_SUBS * FE3_IMG + 2 * 4096 +
-                            (size_t)FE3_SUBS * (2 * FE_MAX_RECS * 4 + FE_THREADS * 4);
-
-__device__ __forceinline__ void sub_barrier(int sub) { asm volatile("bar.sync %0, %1;" ::"r"(sub + 1), "r"(FE_THREADS) : "memory"); }
-
-template <int UNROLL>
-__global__ void __launch_bounds__(FE3_THREADS, 1) k_emit_fast3(FastEmitParams fp) {
-  extern __shared__ __align__(16) uint8_t smem3[];
-  uint32_t *s_tabr = reinterpret_cast<uint32_t *>(smem3);                      // [4][256][32] lane-private
-  uint8_t *s_img_all = smem3 + (size_t)4 * 256 * 32 * 4;
-  uint32_t *s_adv = reinterpret_cast<uint32_t *>(s_img_all + (size_t)FE3_SUBS * FE3_IMG);  // [4][256] * x^(32*(4T-3))
-  uint32_t *s_adv32 = s_adv + 1024;                                                       // [4][256] * x^(32*128)
-  uint32_t *s_idx_all = s_adv32 + 1024;                                                   // [SUBS][2][256]
-  uint32_t *s_part_all = s_idx_all + FE3_SUBS * 2 * FE_MAX_RECS;                          // [SUBS][256]
-
-  const EmitParams &e = fp.e;
-  const int sub = threadIdx.x / FE_THREADS, tid = threadIdx.x % FE_THREADS, lane = tid & 31, warp = tid >> 5;
-  for (int i = threadIdx.x; i < 4 * 256 * 32; i += FE3_THREADS) s_tabr[i] = (&e.crc->slice[0][0])[i >> 5];
-  for (int i = threadIdx.x; i < 4 * 256; i += FE3_THREADS) {
-    s_adv[i] = (&e.crc->advc[0][0])[i];
-    s_adv32[i] = (&e.crc->adv128[0][0])[i];
-  }
-  __syncthreads();
-  uint8_t *s_img = s_img_all + (size_t)sub * FE3_IMG;
-  uint32_t *s_idx0 = s_idx_all + sub * 2 * FE_MAX_RECS;
-  uint32_t *s_part = s_part_all + sub * FE_THREADS;
-  const uint32_t *tabl = s_tabr + lane;  // this lane's bank
-#define TABR(k, b) tabl[(((k) << 8) + (b)) << 5]
-#define S4(x) (TABR(3, (x) & 0xFF) ^ TABR(2, ((x) >> 8) & 0xFF) ^ TABR(1, ((x) >> 16) & 0xFF) ^ TABR(0, (x) >> 24))
-  const uint32_t lane_pow = e.crc->pow_word[4 * (31 - lane)];
-  const uint32_t img_base = (uint32_t)__cvta_generic_to_shared(s_img);
-  const uint8_t *__restrict__ kv = e.rec.kv;
-  const uint32_t rec_size = e.rec_size, hdr_len = e.fixed_hdr_len, stride = fp.stride;
-  const uint32_t first = blockIdx.x * FE3_SUBS + sub, step = gridDim.x * FE3_SUBS;
-
-  TileDesc td_next;
-  if (first < fp.ntiles) {
-    td_next = fp.tiles[first];
-    if ((uint32_t)tid < td_next.nr) s_idx0[tid] = e.order[td_next.r0 + tid];
-  }
-  uint32_t buf = 0;
-  for (uint32_t tile = first; tile < fp.ntiles; tile += step, buf ^= 1u) {
-    const TileDesc td = td_next;
-    const uint32_t nr = td.nr;
-    const bool first_tile = td.flags & 1u, last_tile = td.flags & 2u;
-    const uint32_t tile_n = tile + step;
-    if (tile_n < fp.ntiles) td_next = fp.tiles[tile_n];
-    sub_barrier(sub);  // previous tile of this group fully written out; indices of this tile visible
-    const uint32_t *__restrict__ c_idx = s_idx0 + buf * FE_MAX_RECS;
-    const uint64_t abs0 = td.abs0;
-    const uint32_t lead = (uint32_t)(abs0 & 15u);
-    const uint32_t rec0 = lead + (first_tile ? 4u : 0u);
-    const uint32_t body_end = rec0 + nr * rec_size + (last_tile ? 2u : 0u);
-
-    // ---- gather (see k_emit_fast)
-    const uint32_t npieces = nr * fp.cpr;
-    const uint32_t half_up = (nr + 1) >> 1;
-    for (uint32_t q0 = tid; q0 < npieces; q0 += FE_THREADS * UNROLL) {
-      uint4 v[UNROLL];
-      uint32_t dst[UNROLL];
-#pragma unroll
-      for (int u = 0; u < UNROLL; u++) {
-        uint32_t q = q0 + u * FE_THREADS;
-        if (q < npieces) {
-          uint32_t jp = fp.cpr == 1 ? q : __umulhi(q, fp.cpr_magic);
-          uint32_t c = q - jp * fp.cpr;
-          uint32_t j = jp < half_up ? 2u * jp : 2u * (jp - half_up) + 1u;
-          v[u] = ldg_stream_v4(kv + (uint64_t)c_idx[j] * stride + 16u * c);
-          dst[u] = img_base + rec0 + j * rec_size + hdr_len + 16u * c;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < UNROLL; u++) {
-        uint32_t q = q0 + u * FE_THREADS;
-        if (q < npieces) sts16_unaligned(dst[u], v[u]);
-      }
-    }
-    if (tile_n < fp.ntiles && (uint32_t)tid < td_next.nr) s_idx0[(buf ^ 1u) * FE_MAX_RECS + tid] = e.order[td_next.r0 + tid];
-    if ((uint32_t)tid < nr) {
-      uint32_t a = img_base + rec0 + tid * rec_size;
-      for (uint32_t b = 0; b < hdr_len; b++) sts_b8(a + b, e.fixed_hdr[b]);
-    }
-    if (tid == 0) {
-      if (first_tile) { s_img[lead] = 'T'; s_img[lead + 1] = 'I'; s_img[lead + 2] = 'F'; s_img[lead + 3] = 0; }
-      if (last_tile) { s_img[body_end - 2] = 0xFF; s_img[body_end - 1] = 0xFF; }
-    }
-    sub_barrier(sub);
-
-    // ---- fused CRC + write-out (see k_emit_fast); the S4 look-ups hit the lane's own bank
-    const uint32_t cb0 = rec0, cb1 = body_end;
-    const uint32_t ca = cb0 >> 4, cz = cb1 >> 4;
-    {
-      uint8_t *dstg = e.out + (abs0 - lead);
-      uint32_t c = 0;
-      if (cz > ca) {
-        const uint32_t Cn = cz - ca;
-        if (Cn + tid >= FE_THREADS) {
-          const uint32_t last_i = Cn - FE_THREADS + tid;
-          for (uint32_t i = last_i % FE_THREADS; i <= last_i; i += FE_THREADS) {
-            const uint32_t b0 = 16u * (ca + i);
-            uint4 v = *reinterpret_cast<const uint4 *>(s_img + b0);
-            if (b0 >= lead) stg_stream_v4(dstg + b0, v);
-            else for (uint32_t x = lead; x < b0 + 16u; x++) dstg[x] = s_img[x];
-            if (i == 0 && (cb0 & 15u)) {
-              const uint32_t skip = cb0 & 15u;
-              uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-              for (uint32_t k = 0; k < 4; k++) {
-                if (skip >= 4 * k + 4) w[k] = 0;
-                else if (skip > 4 * k) w[k] &= 0xFFFFFFFFu << (8u * (skip - 4 * k));
-              }
-              v = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            uint32_t x = c ^ v.x;
-            x = S4(x) ^ v.y;
-            x = S4(x) ^ v.z;
-            x = S4(x) ^ v.w;
-            if (i == last_i) c = S4(x);
-            else c = s_adv[x & 0xFF] ^ s_adv[256 + ((x >> 8) & 0xFF)] ^ s_adv[512 + ((x >> 16) & 0xFF)] ^ s_adv[768 + (x >> 24)];
-          }
-        }
-      }
-      s_part[tid] = c;
-      if (tid == 0) {
-        for (uint32_t x = max(lead, 16u * cz); x < body_end; x++) dstg[x] = s_img[x];
-        if (ca > (lead >> 4)) for (uint32_t x = lead; x < 16u * ca; x++) dstg[x] = s_img[x];
-      }
-    }
-    sub_barrier(sub);
-    if (warp == 0) {
-      uint32_t q = 0;
-#pragma unroll
-      for (int k = 0; k < FE_THREADS / 32; k++) {
-        q = s_adv32[q & 0xFF] ^ s_adv32[256 + ((q >> 8) & 0xFF)] ^ s_adv32[512 + ((q >> 16) & 0xFF)] ^ s_adv32[768 + (q >> 24)];
-        q ^= s_part[lane + 32 * k];
-      }
-      q = crc_multmodp(q, lane_pow);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) q ^= __shfl_xor_sync(0xffffffffu, q, o);
-      if (lane == 0) {
-        uint32_t raw = q;
-        if (cz <= ca) {
-          raw = 0;
-          for (uint32_t b = cb0; b < cb1; b++) raw = TABR(0, (raw ^ s_img[b]) & 0xFF) ^ (raw >> 8);
-        } else {
-          for (uint32_t b = 16u * cz; b < cb1; b++) raw = TABR(0, (raw ^ s_img[b]) & 0xFF) ^ (raw >> 8);
-        }
-        TileCrc tc;
-        tc.raw = raw;
-        tc.p = td.p;
-        tc.after = td.after;
-        fp.tile_crc[tile] = tc;
-      }
-    }
-  }
-#undef S4
-#undef TABR
-}
-
 }  // namespace tezgpu

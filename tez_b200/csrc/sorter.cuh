@@ -137,8 +137,8 @@ class SortPipeline {
     for (int b = 0; b < vint_size_u32(rec.vlen); b++) e.fixed_hdr[h++] = vint_byte_u32(rec.vlen, b);
     e.fixed_hdr_len = h;
     e.rec_size = h + rec.klen + rec.vlen;
-    // the tile image must fit the smallest image buffer of the emit kernels (k_emit_fast3: FE3_IMG bytes)
-    e.recs_per_tile = std::max<uint32_t>(1, std::min<uint32_t>(EMIT_MAX_RECS, (FE3_IMG - 32) / e.rec_size));
+    // the tile image must fit the image buffer of the source-oriented emit kernels (FE_IMG_BYTES)
+    e.recs_per_tile = std::max<uint32_t>(1, std::min<uint32_t>(EMIT_MAX_RECS, (FE_IMG_BYTES - 32) / e.rec_size));
     // Round filling: the checksum / write-out loop of the source-oriented kernels walks a tile in rounds of
     // FE_THREADS 16-byte chunks; 256 records of 82 bytes are 5.13 rounds, six are executed.  Among the tile sizes
     // within 10 % of the cap, take the one with the most records per executed round (249 for 82-byte records).
@@ -426,17 +426,7 @@ class SortPipeline {
     if (tiles) {
       if (fast_emit) {
         int per_sm = 0;
-        if (fast_aligned && getenv("TEZGPU_EMIT_V3")) {
-          // experiment (measured slower: 7.75 vs 6.34 ms -- fewer tiles in flight per SM outweigh the conflict-free
-          // look-ups): lane-private CRC tables, three 256-thread groups per SM (k_emit_fast3)
-          static bool attr3 = false;
-          if (!attr3) {
-            TG_CUDA(cudaFuncSetAttribute(k_emit_fast3<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FE3_SMEM));
-            attr3 = true;
-          }
-          uint32_t grid = (uint32_t)std::min<uint64_t>(div_up(tiles, FE3_SUBS), (uint64_t)num_sms);
-          k_emit_fast3<5><<<grid, FE3_THREADS, FE3_SMEM, stream>>>(fp);
-        } else if (fast_aligned && emit4_fits(e.recs_per_tile, fp.cpr) && !getenv("TEZGPU_EMIT_V2")) {
+        if (fast_aligned && emit4_fits(e.recs_per_tile, fp.cpr) && !getenv("TEZGPU_EMIT_V2")) {
           // software-pipelined kernel (emit_pipe.cuh): a tile's pieces must fit the registers of one gather round.
           // Default: independent 256-thread CTAs, three per SM.  TEZGPU_EMIT_SUBS=3 selects the variant with one CTA
           // per SM whose three groups share lane-private checksum tables -- measured SLOWER (8.39 vs 5.44 ms): its
