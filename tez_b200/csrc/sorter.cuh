@@ -11,7 +11,7 @@
 #ifndef TEZGPU_EMIT_ROUND_FILL_DEFAULT
 #define TEZGPU_EMIT_ROUND_FILL_DEFAULT 0
 #endif
-#include "emit_pipe.cuh"
+#include "emit_pipe_u.cuh"
 #include "sorter_kernels.cuh"
 
 namespace tezgpu {
@@ -131,6 +131,10 @@ class SortPipeline {
     e.P = conf.num_partitions;
     return e;
   }
+  static bool pipe_unaligned_enabled() {
+    static const bool on = getenv("TEZGPU_EMIT_PIPE_UNALIGNED") && atoi(getenv("TEZGPU_EMIT_PIPE_UNALIGNED")) != 0;
+    return on;
+  }
   static void set_fixed_layout(EmitParams &e, const Records &rec) {
     int h = 0;
     for (int b = 0; b < vint_size_u32(rec.klen); b++) e.fixed_hdr[h++] = vint_byte_u32(rec.klen, b);
@@ -143,7 +147,18 @@ class SortPipeline {
     // FE_THREADS 16-byte chunks; 256 records of 82 bytes are 5.13 rounds, six are executed.  Among the tile sizes
     // within 10 % of the cap, take the one with the most records per executed round (249 for 82-byte records).
     static const int round_fill = getenv("TEZGPU_EMIT_ROUND_FILL") ? atoi(getenv("TEZGPU_EMIT_ROUND_FILL")) : TEZGPU_EMIT_ROUND_FILL_DEFAULT;
-    if (round_fill && e.recs_per_tile >= 32) {
+    bool fill = round_fill != 0;
+    if (pipe_unaligned_enabled()) {
+      // the pipelined kernel for records at arbitrary offsets (emit_pipe_u.cuh) holds a tile's words in five gather rounds
+      const uint32_t stride = rec.klen + rec.vlen;
+      const bool fast = stride >= 16 && stride % 16 == 0;
+      const bool aligned = !rec.key_off && (((uintptr_t)rec.kv & 15u) == 0);
+      if (fast && !aligned && emit4u_max_recs(stride / 16) >= 32) {
+        e.recs_per_tile = std::min<uint32_t>(e.recs_per_tile, emit4u_max_recs(stride / 16));
+        fill = true;
+      }
+    }
+    if (fill && e.recs_per_tile >= 32) {
       const uint32_t cap = e.recs_per_tile;
       uint32_t best = cap;
       double best_eff = 0;
@@ -455,6 +470,16 @@ class SortPipeline {
           TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_fast<5, true>, FE_THREADS, 0));
           uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));
           k_emit_fast<5, true><<<grid, FE_THREADS, 0, stream>>>(fp);
+        } else if (!fast_aligned && pipe_unaligned_enabled() && e.recs_per_tile <= emit4u_max_recs(fp.cpr)) {
+          // records at arbitrary offsets (reduce side), software-pipelined variant -- opt-in until measured
+          static bool attr = false;
+          if (!attr) {
+            TG_CUDA(cudaFuncSetAttribute(k_emit_fast4u<FE4U_UNROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Emit4uSmem::TOTAL));
+            attr = true;
+          }
+          TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_fast4u<FE4U_UNROLL>, FE_THREADS, Emit4uSmem::TOTAL));
+          uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));
+          k_emit_fast4u<FE4U_UNROLL><<<grid, FE_THREADS, Emit4uSmem::TOTAL, stream>>>(fp);
         } else {
           TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_fast<5, false>, FE_THREADS, 0));
           uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));
