@@ -118,6 +118,45 @@ def run_cpu(cores, per_task, steps, warmup, partitions):
     return n * REC / t / 1e9, t, n
 
 
+class gpu_local_cpus:
+    """Pins the calling thread (and the threads it starts) to the CPUs NVML reports as local to a GPU while the pinned
+    host buffers of the e2e leg are allocated (first touch decides their NUMA node) and copied, then restores the mask.
+    Host memory on the far socket costs PCIe copies a hop over the inter-socket link.  Best effort: any failure
+    leaves the affinity untouched."""
+
+    def __init__(self, device_index=0):
+        self.device_index, self.old, self.cpus = device_index, None, None
+
+    def __enter__(self):
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:
+                pr = torch.cuda.get_device_properties(self.device_index)
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(("%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.device_index)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+            local = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+            old = os.sched_getaffinity(0)
+            cpus = local & old
+            if cpus and cpus != old:
+                os.sched_setaffinity(0, cpus)
+                self.old, self.cpus = old, cpus
+        except Exception:
+            self.old = None
+        return self
+
+    def __exit__(self, *a):
+        if self.old is not None:
+            try:
+                os.sched_setaffinity(0, self.old)
+            except Exception:
+                pass
+        return False
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -227,43 +266,44 @@ def single_gpu(args):
     # step overlaps the D2H of the other on the full-duplex PCIe link.  Every step still copies its own input and output.
     e2e = None
     if not args.no_e2e:
-        slots = 2
-        h_kv = torch.empty(n * REC, dtype=torch.uint8, pin_memory=True)
-        h_kv.copy_(d_kv)
-        h_outs = [torch.empty(cap + 4096, dtype=torch.uint8, pin_memory=True) for _ in range(slots)]
-        torch.cuda.synchronize()
-        sorters = [T.GpuSorter(P, fixed=(KEY_LEN, VAL_LEN), device=0) for _ in range(slots)]
-        esteps = max(slots, min(args.steps, args.e2e_steps))
-        esteps -= esteps % slots
-        out_bytes = [0] * slots
+        with gpu_local_cpus(0) as numa:
+            slots = 2
+            h_kv = torch.empty(n * REC, dtype=torch.uint8, pin_memory=True)
+            h_kv.copy_(d_kv)
+            h_outs = [torch.empty(cap + 4096, dtype=torch.uint8, pin_memory=True) for _ in range(slots)]
+            torch.cuda.synchronize()
+            sorters = [T.GpuSorter(P, fixed=(KEY_LEN, VAL_LEN), device=0) for _ in range(slots)]
+            esteps = max(slots, min(args.steps, args.e2e_steps))
+            esteps -= esteps % slots
+            out_bytes = [0] * slots
 
-        def e2e_worker(k, nsteps):
-            s2, ho = sorters[k], h_outs[k].numpy()
-            for _ in range(nsteps):
-                s2.reset()
-                s2.collect_fixed(h_kv.data_ptr(), n=n)
-                out, _, _, _ = s2.flush_to_memory(out=ho)
-                out_bytes[k] = int(len(out))
+            def e2e_worker(k, nsteps):
+                s2, ho = sorters[k], h_outs[k].numpy()
+                for _ in range(nsteps):
+                    s2.reset()
+                    s2.collect_fixed(h_kv.data_ptr(), n=n)
+                    out, _, _, _ = s2.flush_to_memory(out=ho)
+                    out_bytes[k] = int(len(out))
 
-        def run_e2e(nsteps_per_slot):
-            ths = [threading.Thread(target=e2e_worker, args=(k, nsteps_per_slot)) for k in range(slots)]
-            for t in ths:
-                t.start()
-            for t in ths:
-                t.join()
+            def run_e2e(nsteps_per_slot):
+                ths = [threading.Thread(target=e2e_worker, args=(k, nsteps_per_slot)) for k in range(slots)]
+                for t in ths:
+                    t.start()
+                for t in ths:
+                    t.join()
 
-        run_e2e(1)  # warm-up: allocations, pinning
-        t0 = time.perf_counter()
-        run_e2e(esteps // slots)
-        torch.cuda.synchronize()
-        t = (time.perf_counter() - t0) / esteps
-        e2e = {"value": round(n * REC / t / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": n * REC,
-               "d2h_bytes_per_step": out_bytes[0], "ms_per_step": round(t * 1e3, 2), "steps": esteps,
-               "task_slots": slots,
-               "api": "tezgpu_sorter_collect_fixed + tezgpu_sorter_flush_to_memory (pinned host buffers), 2 task slots"}
-        for s2 in sorters:
-            s2.close()
-        del h_kv, h_outs
+            run_e2e(1)  # warm-up: allocations, pinning
+            t0 = time.perf_counter()
+            run_e2e(esteps // slots)
+            torch.cuda.synchronize()
+            t = (time.perf_counter() - t0) / esteps
+            e2e = {"value": round(n * REC / t / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": n * REC,
+                   "d2h_bytes_per_step": out_bytes[0], "ms_per_step": round(t * 1e3, 2), "steps": esteps,
+                   "task_slots": slots, "host_cpus_pinned_to_gpu_numa_node": len(numa.cpus) if numa.cpus else None,
+                   "api": "tezgpu_sorter_collect_fixed + tezgpu_sorter_flush_to_memory (pinned host buffers), 2 task slots"}
+            for s2 in sorters:
+                s2.close()
+            del h_kv, h_outs
 
     # ---- CPU baseline on this box's host cores (bounded sample)
     cores = min(host_cores(), 128)
