@@ -107,3 +107,34 @@ def test_pull_plan_and_segment_table_resolve_to_the_right_bytes():
             else:
                 got = recv[ptr - recv_base: ptr - recv_base + ln]
             assert np.array_equal(got, files[g][s0:s0 + l0])
+
+
+def _peer_unavailable_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tez_b200 import shuffle
+    try:
+        shuffle.PeerExchange(1 << 20, 0)
+        ret[rank] = "constructed"
+    except RuntimeError as e:
+        ret[rank] = "RuntimeError: %s" % e
+    # the group is still usable: nobody is stuck in a collective the others skipped
+    t = torch.tensor([rank + 1])
+    dist.all_reduce(t)
+    ret["sum%d" % rank] = int(t.item())
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="exercises the no-device failure path")
+def test_peer_exchange_fails_on_every_rank_or_none():
+    """Without a device the exportable buffer cannot be allocated: every rank must raise (consensus) so that a caller
+    can fall back to exchange_partitions() with the process group intact."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_peer_unavailable_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret[r].startswith("RuntimeError: peer pull unavailable"), ret[r]
+        assert ret["sum%d" % r] == 3

@@ -37,7 +37,12 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
     # shuffle transport: "peer" = consumers pull file.out ranges out of the producers' HBM with libtezgpu's fetch kernel
     # (CUDA IPC mappings over NVLink); "nccl" = one variable-size all-to-all of NCCL send/recv pairs (the baseline)
     transport = os.environ.get("TEZ_SHUFFLE", "peer")
-    px = shuffle.PeerExchange(cap, local) if transport == "peer" else None
+    px = None
+    if transport == "peer":
+        try:
+            px = shuffle.PeerExchange(cap, local)
+        except RuntimeError as e:   # raised on every rank or on none (consensus inside)
+            transport = "nccl (%s)" % e
     d_out = None if px else torch.empty(cap, dtype=torch.uint8, device=dev)
     step_no = [0]
     d_merged = torch.empty(int(cap * 1.3) + (1 << 20), dtype=torch.uint8, device=dev)

@@ -122,21 +122,40 @@ class PeerExchange:
         from . import native
         self.group, self.device = group, device
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.slots = [native.PeerBuffer(out_capacity, device) for _ in range(slots)]
         self.capacity = int(out_capacity)
-        handles = [None] * self.world
-        dist.all_gather_object(handles, [b.handle for b in self.slots], group=group)
-        self.peers = []  # peers[g][slot] -> device address of rank g's slot in this process
-        self._maps = []
-        for g in range(self.world):
-            if g == self.rank:
-                self.peers.append([b.ptr for b in self.slots])
-            else:
-                maps = [native.PeerMapping(h, device) for h in handles[g]]
-                self._maps += maps
-                self.peers.append([m.ptr for m in maps])
+        self.slots, self._maps, self.peers = [], [], []
         self._recv = None
         self.last_fetch_ms = 0.0
+        # every phase ends in a consensus (all-reduce MIN of a success flag): either all ranks get the peer transport
+        # or all of them raise, so a caller can fall back to exchange_partitions() without a collective mismatch
+        err = None
+        try:
+            self.slots = [native.PeerBuffer(out_capacity, device) for _ in range(slots)]
+        except Exception as e:  # noqa: BLE001 -- reported through the consensus below
+            err = e
+        self._consensus(err, "allocate an exportable file.out buffer")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, [b.handle for b in self.slots], group=group)
+        try:
+            for g in range(self.world):   # peers[g][slot] -> device address of rank g's slot in this process
+                if g == self.rank:
+                    self.peers.append([b.ptr for b in self.slots])
+                else:
+                    maps = [native.PeerMapping(h, device) for h in handles[g]]
+                    self._maps += maps
+                    self.peers.append([m.ptr for m in maps])
+        except Exception as e:  # noqa: BLE001
+            err = e
+        self._consensus(err, "map a peer's file.out buffer")
+
+    def _consensus(self, err, what):
+        on_dev = dist.get_backend(self.group) == "nccl"
+        flag = torch.tensor([0 if err is not None else 1], dtype=torch.int32,
+                            device=torch.device("cuda", self.device) if on_dev else torch.device("cpu"))
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            self.close()
+            raise RuntimeError("peer pull unavailable: some rank could not %s%s" % (what, (" (%s)" % err) if err else ""))
 
     def out_ptr(self, step):
         return self.slots[step % len(self.slots)].ptr
