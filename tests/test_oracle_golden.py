@@ -309,3 +309,58 @@ def test_pipelined_sort_random_vs_python_sorted():
     assert bytes(out) == r["file_out"]
     assert not r["rle_used"] and r["eq"] == 0
     del rng
+
+
+def test_ordered_word_count_known_answer_through_the_oracle():
+    """TestTezJobs.generateOrderedWordCountInput / verifyOutput (tez-tests/.../TestTezJobs.java:748-805):
+    words a_1..a_10 with counts 20,18,..,2.  Three tokenizer tasks sort (Text word, IntWritable 1) into 4 partitions,
+    each summation task merges its partition of every producer and groups equal keys, a second ordered edge sorts
+    (IntWritable count, Text word) -- the whole map-sort / merge / group path on the CPU restatement."""
+    import random
+    words = []
+    for i in range(1, 11):
+        words += ["a_%d" % i] * (22 - 2 * i)
+    random.Random(3).shuffle(words)
+    P = 4
+
+    def sort_records(records, cmp_kind, nparts):
+        kv = bytearray()
+        ko, kl, vl = [], [], []
+        for k, v in records:
+            ko.append(len(kv)); kl.append(len(k)); vl.append(len(v))
+            kv += k + v
+        return O.pipelined_sort(O.sorter_conf(nparts, cmp_kind=cmp_kind), np.frombuffer(bytes(kv), np.uint8),
+                                np.array(ko, np.uint64), np.array(kl, np.uint32), np.array(vl, np.uint32))
+
+    producers = [sort_records([(O.text(w), O.int_writable(1)) for w in words[t::3]], O.CMP_TEXT, P) for t in range(3)]
+    counts, seen = {}, 0
+    for p in range(P):
+        runs = []
+        for r in producers:
+            start, _, part = (int(x) for x in r["index"][p])
+            if part:
+                runs.append(r["file_out"][start:start + part])
+        if not runs:
+            continue
+        merged = O.merge(runs, O.CMP_TEXT, factor=100)
+        prev = None
+        for key, val, same in merged["records"]:
+            word = key[1:].decode()
+            if prev is None or key != prev:
+                assert word not in counts          # a key's records are contiguous: ValuesIterator grouping
+                counts[word] = 0
+            assert same == (prev is not None and key == prev)
+            counts[word] += int.from_bytes(val, "big")
+            prev = key
+            seen += 1
+    assert seen == len(words)
+    assert counts == {"a_%d" % i: 22 - 2 * i for i in range(1, 11)}
+    # every word went to the partition HashPartitioner assigns to its Text key
+    for r in producers:
+        for p in range(P):
+            start, _, part = (int(x) for x in r["index"][p])
+            for _, key, _ in O.read_ifile(r["file_out"][start:start + part]) if part else []:
+                assert O.partition_of(O.CMP_TEXT, key, P) == p
+    second = sort_records([(O.int_writable(c), O.text(w)) for w, c in counts.items()], O.CMP_INT, 1)
+    final = [(int.from_bytes(k, "big", signed=True), v[1:].decode()) for _, k, v in O.read_ifile(second["file_out"])]
+    assert final == [(22 - 2 * i, "a_%d" % i) for i in range(10, 0, -1)]
