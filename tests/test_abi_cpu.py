@@ -14,3 +14,29 @@ def test_tiled_crc_algebra_matches_zlib():
         for piece in (64, 1040, 24 * 1024):
             for lead in (0, 1, 7, 12, 15):
                 assert L.tezgpu_debug_crc_emulate(d, n, piece, lead) == zlib.crc32(d), (n, piece, lead)
+
+
+def test_segment_table_fast_path_matches_ctypes_layout():
+    """GpuMerger builds the tezgpu_segment table through numpy when there are many device-resident runs; the bytes must
+    equal what the ctypes structure assignment produces (include/tezgpu.h: data, len, flags, partition)."""
+    import ctypes as C
+    import numpy as np
+    from tez_b200 import native
+    from tez_b200._lib import Segment
+    rng = np.random.default_rng(1)
+    n = 200
+    segs = [(int(a), int(b)) for a, b in zip(rng.integers(1 << 33, 1 << 47, n), rng.integers(10, 1 << 30, n))]
+    parts = [int(p) for p in rng.integers(0, 128, n)]
+    m = object.__new__(native.GpuMerger)          # no device needed: only the table builder is exercised
+    m._has_header, m._device_ptrs, m.h = True, True, None
+    fast = m._segments(segs, parts)
+    fast_bytes = C.string_at(fast, n * C.sizeof(Segment))
+    slow = (Segment * n)()
+    for i, (p, ln) in enumerate(segs):
+        slow[i].data, slow[i].len = p, ln
+        slow[i].flags = native.SEG_HAS_HEADER | native.SEG_DEVICE
+        slow[i].partition = parts[i]
+    assert C.sizeof(Segment) == 24
+    assert fast_bytes == bytes(slow)
+    few = m._segments(segs[:3], parts[:3])        # the ctypes path (<= 64 runs)
+    assert bytes(few)[:3 * 24] == bytes(slow)[:3 * 24]
