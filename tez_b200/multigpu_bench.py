@@ -90,6 +90,54 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
             phase_ms["merge"].append(e[2].elapsed_time(e[3]))
         return nrec, mlen
 
+    # TEZ_SHUFFLE_OVERLAP=1 (opt-in, written at the end of round 1, not yet measured): the NVLink-bound pull of batch k
+    # runs concurrently with the HBM-bound sort of batch k+1 (second host thread, own stream).  The sort of batch k+1
+    # starts only after the index all-gather of batch k returned: by then every peer has finished pulling batch k-1,
+    # whose buffer the sort rewrites.  Every iteration still performs one sort, one exchange and one merge.
+    overlap = px is not None and os.environ.get("TEZ_SHUFFLE_OVERLAP", "0") == "1"
+    if overlap:
+        import threading
+        pull_stream = torch.cuda.Stream(device=dev)
+        pending = {}
+
+        def sort_batch(k):
+            out_len, index, st = sorter.sort_device_fixed(d_kv.data_ptr(), n, px.out_ptr(k), cap)
+            pending[k] = (index, st)
+
+        sort_batch(0)          # batch 0 is sorted before the pipeline starts; batch K is sorted inside it
+
+        def step(timed):       # noqa: F811 -- replaces the sequential step
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            k = step_no[0]
+            step_no[0] += 1
+            index, st = pending.pop(k)
+            all_idx = px.gather(index)
+            th = threading.Thread(target=sort_batch, args=(k + 1,))
+            th.start()
+            segs = px.pull(k, all_idx, P, stream=pull_stream.cuda_stream)
+            th.join()
+            e[1].record()
+            seg_list = [(ptr, ln) for ptr, ln, _, _ in segs]
+            parts = [p for _, _, p, _ in segs]
+            if merger[0] is None:
+                merger[0] = T.GpuMerger(seg_list, comparator=T.CMP_BYTES, device=local, device_ptrs=True,
+                                        fixed=(KEY_LEN, VAL_LEN), partitions=parts, num_partitions=p1 - p0)
+            else:
+                merger[0].reopen(seg_list, parts)
+            m = merger[0]
+            mlen, mindex, mst = m.write_partitions_device(d_merged.data_ptr(), d_merged.numel())
+            nrec, _ = m.counts()
+            e[2].record()
+            if timed:
+                torch.cuda.synchronize()
+                launches[0] += st["kernel_launches"] + mst["kernel_launches"]
+                fetch_ms.append(px.last_fetch_ms)
+                phase_ms["sort"].append(0.0)
+                phase_ms["exchange"].append(e[0].elapsed_time(e[1]))   # gather + max(pull k, sort k+1)
+                phase_ms["merge"].append(e[1].elapsed_time(e[2]))
+            return nrec, mlen
+
     for _ in range(args.warmup):
         step(False)
     clocks = ClockSampler(local)
@@ -135,7 +183,7 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
                            "achieved_GBps_per_gpu": round(sent / (avg["exchange"] * 1e-3) / 1e9, 1) if avg["exchange"] else None,
                            "fetch_kernel_ms": round(sum(fetch_ms) / len(fetch_ms), 3) if fetch_ms else None,
                            "fetch_kernel_GBps_per_gpu": round(sent / (sum(fetch_ms) / len(fetch_ms) * 1e-3) / 1e9, 1) if fetch_ms and sum(fetch_ms) else None,
-                           "transport": transport, "reference_GBps": 770,
+                           "transport": transport + (" + sort(k+1) overlapped with pull(k)" if overlap else ""), "reference_GBps": 770,
                            "note": ("peer pull: index all-gather (NCCL) + one fetch kernel over CUDA IPC mappings; own partitions merged in place"
                                     if px else "variable-size all-to-all (NCCL send/recv) incl. index all-gather")},
                 "roofline": {"bound": "hbm", "achieved": round(n * (2 * 162) / (ms_step * 1e-3) / 1e9, 1), "peak": peak,

@@ -164,15 +164,24 @@ class PeerExchange:
         """index: this rank's [P,3] spill index of the file.out it just wrote into slot `step`.
         Returns segments [(device_ptr, length, local_partition, source_rank)] ordered by (source_rank, partition):
         own segments point into the local slot, the others into the receive buffer the pull kernel filled."""
+        return self.pull(step, self.gather(index), num_partitions)
+
+    def gather(self, index):
+        """The collective half of exchange(): all-gather of the spill index.  When it returns, every rank has entered
+        it, i.e. has finished pulling the previous step."""
+        return _gather_index(index, self.group, torch.device("cuda", self.device))
+
+    def pull(self, step, all_idx, num_partitions, stream=None):
+        """The data half of exchange(): one fetch kernel (on `stream`, a raw cudaStream_t handle, default stream when
+        None) pulls this rank's partitions of step `step` from every peer; returns the segment table once they landed."""
         from . import native
         slot = step % len(self.slots)
-        all_idx = _gather_index(index, self.group, torch.device("cuda", self.device))
         peer_ptrs = [self.peers[g][slot] for g in range(self.world)]
         ranges, seg_src, need = pull_plan(all_idx, self.rank, num_partitions, peer_ptrs)
         if self._recv is None or self._recv.numel() < need + 64:
             self._recv = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, device=torch.device("cuda", self.device))
         base = self._recv.data_ptr()
-        self.last_fetch_ms = native.fetch_ranges([(src, base + off, ln) for _, src, off, ln in ranges], self.device)
+        self.last_fetch_ms = native.fetch_ranges([(src, base + off, ln) for _, src, off, ln in ranges], self.device, stream)
         return pull_segments(all_idx, self.rank, num_partitions, peer_ptrs, seg_src, base)
 
     def close(self):
