@@ -16,7 +16,9 @@ constexpr uint32_t CRC_POLY = 0xEDB88320u;
 // a(x) * b(x) mod P, reflected representation (bit 31 = x^0)
 __host__ __device__ __forceinline__ uint32_t crc_multmodp(uint32_t a, uint32_t b) {
   uint32_t p = 0;
+#ifdef __CUDA_ARCH__
 #pragma unroll 4
+#endif
   for (int i = 0; i < 32; i++) {
     p ^= b & (0u - ((a >> (31 - i)) & 1u));
     b = (b >> 1) ^ (CRC_POLY & (0u - (b & 1u)));

@@ -109,18 +109,6 @@ static std::vector<uint8_t> read_file(const std::string &p, uint64_t off = 0, in
   ::close(fd);
   return b;
 }
-static void write_file_0640(const std::string &p, const void *d, size_t n) {
-  int fd = ::open(p.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0640);  // SPILL_FILE_PERMS (SORT/TezSpillRecord.java:41)
-  RT_CHECK(fd >= 0, TEZGPU_E_IO, "open " + p + ": " + strerror(errno));
-  const uint8_t *q = (const uint8_t *)d;
-  while (n) {
-    ssize_t w = ::write(fd, q, n);
-    if (w < 0) { ::close(fd); throw Err(TEZGPU_E_IO, "write " + p + ": " + strerror(errno)); }
-    q += w; n -= (size_t)w;
-  }
-  ::fchmod(fd, 0640);
-  ::close(fd);
-}
 // TezCommonUtils.compressByteArrayToByteString with newBestCompressionDeflater(): raw deflate, level 9
 static std::string deflate_raw(const std::vector<uint8_t> &in) {
   z_stream z;

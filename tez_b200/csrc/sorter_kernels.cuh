@@ -209,14 +209,14 @@ __global__ void __launch_bounds__(SCAN_THREADS)
                uint32_t *__restrict__ m_out) {
   __shared__ uint32_t s_k[SCAN_TILE + 2];
   __shared__ uint32_t s_ct[SCAN_IPT][SCAN_THREADS / 32], s_ch[SCAN_IPT][SCAN_THREADS / 32];
-  __shared__ uint32_t s_tile;
   __shared__ uint64_t s_base;
 #ifdef TEZGPU_TICKET_ATOMIC
+  __shared__ uint32_t s_tile;
   if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
   __syncthreads();
   const uint32_t tile = s_tile;
 #else
-  (void)ticket; (void)s_tile;
+  (void)ticket;
   const uint32_t tile = blockIdx.x;  // in-order dispatch of a 1-D grid (see radix_sort.cuh)
 #endif
   TileFlags f;
