@@ -67,6 +67,12 @@ int32_t tezrt_input_start(tezrt_input *in);
  * the partition empty in its event's bitmap (no fetch). */
 int32_t tezrt_input_add_local_output(tezrt_input *in, int32_t source_index, const char *file_out,
                                      const char *index_file, int32_t partition, int32_t empty);
+/* the same for a producer running with tez.runtime.enable.final-merge.in.output=false (pipelined shuffle): one event per
+ * spill, carrying spill_id and last_event_flag (ShufflePayloads.proto DataMovementEventPayloadProto fields 9 and 8;
+ * OG/ShuffleInputEventHandlerOrderedGrouped.java:225-240, OG/ShuffleScheduler.java:540-600).  The source counts as delivered once the event flagged last
+ * and every spill id below it have arrived; duplicates are ignored. */
+int32_t tezrt_input_add_local_spill(tezrt_input *in, int32_t source_index, const char *file_out, const char *index_file,
+                                    int32_t partition, int32_t empty, int32_t spill_id, int32_t last_event);
 /* waitForInputReady(): all physical inputs delivered -> final merge on the device */
 int32_t tezrt_input_wait_ready(tezrt_input *in);
 /* getReader(): KeyValuesReader.next() -> 1 when a new key group is available, 0 at the end */

@@ -163,6 +163,12 @@ int32_t tezgpu_merge_open(const tezgpu_conf *conf, const tezgpu_segment *segs, u
 /* runs a new merge through an existing handle, keeping its device allocations (the per-step reduce side of the
  * multi-GPU shuffle; a container-reused task) */
 int32_t tezgpu_merge_reopen(tezgpu_merger *m, const tezgpu_segment *segs, uint32_t nseg);
+/* MergeQueue's checkForSameKeys constructor argument (SORT/TezMerger.java:560-573; default true like the reference's
+ * other constructors, :519).  When 0, isSameKey() -- and therefore REPEAT_KEY in tezgpu_merge_write_* -- is reported
+ * only for records that were run-length encoded in their input segment, never across segment boundaries
+ * (adjustPriorityQueue / compareKeyWithNextTopKey, :597-652).  PipelinedSorter's final merge passes
+ * merger.needsRLE() here AND as the writer's rle (SORT/PipelinedSorter.java:797-814).  Call before next_batch / write. */
+int32_t tezgpu_merge_set_check_for_same_keys(tezgpu_merger *m, int32_t check_for_same_keys);
 /* total records / key+value bytes of the merged stream */
 int32_t tezgpu_merge_counts(tezgpu_merger *m, uint64_t *records, uint64_t *kv_bytes);
 /* replaces the next()/getKey()/getValue()/isSameKey() loop: fills up to idx_cap records (key||value bytes appended to

@@ -13,8 +13,10 @@ from test_oracle_golden import MERGER_TABLES, _ifile_with_text_data
 pytestmark = pytest.mark.gpu
 
 
-def _gpu_merge(segs, cmp_kind, has_header=True, fixed=None, writer_rle=False):
+def _gpu_merge(segs, cmp_kind, has_header=True, fixed=None, writer_rle=False, check_for_same_keys=True):
     with T.GpuMerger(segs, comparator=cmp_kind, has_header=has_header, fixed=fixed) as m:
+        if not check_for_same_keys:
+            m.set_check_for_same_keys(False)
         nrec, kvb = m.counts()
         recs = list(m.records(batch_records=1000, batch_bytes=1 << 16))
         assert len(recs) == nrec
@@ -196,3 +198,42 @@ def test_merger_reopen_and_large_runs_through_the_staged_parser():
         seg, raw, part, _ = m.write_ifile()
         assert seg == exp["ifile"]
         assert m.counts()[0] == len(exp["records"])
+
+
+@pytest.mark.parametrize("inputs_rle", [False, True])
+@pytest.mark.parametrize("dup_pct", [1, 5, 9, 30])
+def test_check_for_same_keys_and_writer_rle_grid(inputs_rle, dup_pct):
+    """MergeQueue(checkForSameKeys) x IFile.Writer(rle) (SORT/TezMerger.java:560-573,597-652; callers
+    SORT/PipelinedSorter.java:797-814): duplicate keys inside and across >= 3 segments, value = f(key).  With
+    checkForSameKeys off, isSameKey() is only what the input segments' own run-length encoding says."""
+    rng = random.Random(1000 * dup_pct + inputs_rle)
+    nseg, per = 5, 4000
+    pool = [rng.getrandbits(64).to_bytes(8, "big") for _ in range(nseg * per)]
+    segs = []
+    for s in range(nseg):
+        keys = [pool[rng.randrange(len(pool))] for _ in range(per)]
+        ndup = per * dup_pct // 100
+        keys += [keys[rng.randrange(per)] for _ in range(ndup // 2)]                 # duplicates inside the segment
+        keys += [pool[rng.randrange(len(pool))] for _ in range(ndup - ndup // 2)]    # and (likely) across segments
+        keys.sort()
+        segs.append(O.write_ifile([(k, zlib.crc32(k).to_bytes(4, "big") * (1 + k[0] % 3)) for k in keys], rle=inputs_rle)[0])
+    shared = set(k for _, k, _ in O.read_ifile(segs[0]) if k) & set(k for _, k, _ in O.read_ifile(segs[1]))
+    for check in (True, False):
+        for writer_rle in (False, True):
+            exp = O.merge(segs, O.CMP_BYTES, factor=100, check_for_same_keys=check, writer_rle=writer_rle)
+            recs, seg = _gpu_merge(segs, T.CMP_BYTES, writer_rle=writer_rle, check_for_same_keys=check)
+            assert [(k, v) for k, v, _ in recs] == [(k, v) for k, v, _ in exp["records"]]
+            assert [s for _, _, s in recs] == [s for _, _, s in exp["records"]], (check, writer_rle)
+            assert seg == exp["ifile"], (check, writer_rle)
+            if not check and not writer_rle and not inputs_rle:   # nothing is a repeat: no RLE / V_END markers in the output
+                assert not any(s for _, _, s in recs)
+                assert all(ks == O.NEW_KEY for ks, _, _ in O.read_ifile(seg))
+            if check and shared:                                  # equal keys of different segments ARE flagged
+                assert any(s for _, _, s in recs)
+
+
+def test_write_ifile_on_a_multi_partition_merger_is_rejected():
+    segs = [O.write_ifile([(b"a", b"1")])[0], O.write_ifile([(b"b", b"2")])[0]]
+    with T.GpuMerger(segs, comparator=T.CMP_BYTES, partitions=[0, 1], num_partitions=2) as m:
+        with pytest.raises(IOError, match="num_partitions"):
+            m.write_ifile()

@@ -98,6 +98,84 @@ def test_multiple_spills_and_final_merge_match_single_sort(tmp_path):
     assert not os.path.exists(str(tmp_path / "output" / (out.context.unique_identifier + "_0")))   # spill dirs removed
 
 
+@pytest.mark.parametrize("dup_pct", [1, 5, 9, 30])
+def test_multi_spill_final_merge_with_duplicate_keys(tmp_path, dup_pct):
+    """PipelinedSorter.flush final merge with duplicate keys (SORT/PipelinedSorter.java:797-814): checkForSameKeys AND the
+    writer's rle are both merger.needsRLE() of the last spill.  <= 10 % duplicates: no spill and no merge output is
+    run-length encoded (no FE/FD markers at all); 30 %: every adjacent equal key is.  value = f(key), so the bytes are
+    determined; the oracle's single-span sorter gives the same RLE decision at these levels (eq = 1.03 x duplicates)."""
+    n, P = 60000, 8
+    rng = random.Random(dup_pct)
+    nd = n * dup_pct // 100
+    base = [bytes(r[:16]) for r in O.gen_c2(0, n - nd, seed=17).reshape(-1, 80)]
+    keys = base + [base[rng.randrange(len(base))] for _ in range(nd)]
+    rng.shuffle(keys)
+    recs = [(k, zlib.crc32(k).to_bytes(4, "big") * 16) for k in keys]
+    conf = {"tez.runtime.key.class": BYTES_WRITABLE, "tez.runtime.key.comparator.class": TEZ_BYTES_COMPARATOR,
+            "tez.runtime.io.sort.mb": 1}
+    out, events = _run_output(tmp_path, conf, recs, P)
+    assert out.num_spills >= 4
+    kv = np.frombuffer(b"".join(k + v for k, v in recs), dtype=np.uint8)
+    rle = dup_pct > 10
+    exp = O.pipelined_sort_fixed(O.sorter_conf(P, rle_policy=1 if rle else 0), kv, 16, 64)
+    got = open(out.final_output_file, "rb").read()
+    assert got == exp["file_out"]
+    assert open(out.final_index_file, "rb").read() == exp["index_out"]
+    idx = np.frombuffer(open(out.final_index_file, "rb").read()[:-8], dtype=">i8").reshape(P, 3)
+    states = [ks for p in range(P) for ks, _, _ in O.read_ifile(got[idx[p, 0]:idx[p, 0] + idx[p, 2]])]
+    assert len(states) == n and (O.SAME_KEY in states) == rle      # <= 10 %: not one RLE / V_END marker in file.out
+    assert out.counter("OUTPUT_RECORDS") == n and out.counter("SPILLED_RECORDS") == 2 * n
+
+
+def test_pipelined_shuffle_spill_events_reach_the_input(tmp_path):
+    """tez.runtime.enable.final-merge.in.output=false: one CompositeDataMovementEvent per spill (spill_id, last_event);
+    the input must fetch EVERY spill of a producer and only then report ready (OG/ShuffleScheduler.java:540-600)."""
+    n, P = 40000, 4
+    kv = O.gen_c2(0, n, seed=23)
+    recs = [(bytes(r[:16]), bytes(r[16:])) for r in kv.reshape(n, 80)]
+    conf = {"tez.runtime.key.class": BYTES_WRITABLE, "tez.runtime.key.comparator.class": TEZ_BYTES_COMPARATOR,
+            "tez.runtime.io.sort.mb": 1, "tez.runtime.enable.final-merge.in.output": False,
+            "tez.runtime.report.partition.stats": "precise"}
+    out, events = _run_output(tmp_path, conf, recs, P)
+    S = out.num_spills
+    assert S >= 3
+    dms = [e for e in events if e.type == "CompositeDataMovementEvent"]
+    assert len(dms) == S
+    spill_ids = [parse_proto(e.payload)[9][0] for e in dms]
+    lasts = [parse_proto(e.payload)[8][0] for e in dms]
+    assert spill_ids == list(range(S)) and lasts == [0] * (S - 1) + [1]
+    # the single VertexManagerEvent reports the sizes accumulated over every spill (partitionStats)
+    vms = [e for e in events if e.type == "VertexManagerEvent"]
+    assert len(vms) == 1
+    sizes_mb = list(parse_proto(parse_proto(vms[0].payload)[3][0])[1][0])
+    uid = out.context.unique_identifier
+    files = [str(tmp_path / "output" / ("%s_%d" % (uid, s)) / "file.out") for s in range(S)]
+    idxs = [np.frombuffer(open(f + ".index", "rb").read()[:-8], dtype=">i8").reshape(P, 3) for f in files]
+    total_raw = sum(ix[:, 1] for ix in idxs)
+    assert sizes_mb == [int((r + (1 << 20) - 1) >> 20) for r in total_raw]
+    p = 2
+    inp = OrderedGroupedKVInput(InputContext(conf, str(tmp_path / "r")), 1)
+    inp.initialize()
+    inp.start()
+    order = list(range(S))
+    random.Random(5).shuffle(order)          # events may arrive in any order; duplicates are ignored
+    for k, s_id in enumerate(order):
+        lo = LocalOutput(0, files[s_id], files[s_id] + ".index", p, spill_id=s_id, last_event=(s_id == S - 1))
+        if k < S - 1:
+            inp.handleEvents([lo, lo])
+            with pytest.raises(IOError, match="have not been delivered"):
+                inp.waitForInputReady()
+        else:
+            inp.handleEvents([lo])
+    r = inp.getReader()
+    got = []
+    while r.next():
+        got.append((r.getCurrentKey(), list(r.getCurrentValues())))
+    mine = sorted((k, v) for k, v in recs if O.partition_of(O.CMP_BYTES, k, P) == p)
+    assert [(k, vs[0]) for k, vs in got] == mine and all(len(vs) == 1 for _, vs in got)
+    assert inp.counter("NUM_SHUFFLED_INPUTS") == S
+
+
 def test_custom_partitioner_results_are_passed_through(tmp_path):
     conf = {"tez.runtime.key.class": INT_WRITABLE, "tez.runtime.partitioner.class": "org.example.RangePartitioner"}
     ctx = OutputContext(conf, str(tmp_path))

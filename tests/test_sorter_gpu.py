@@ -77,6 +77,25 @@ def test_c2_fixed_width_bit_exact(n, P):
     assert st["output_bytes"] == n * 80
 
 
+@pytest.mark.parametrize("n", [1_000_000, 10_000_000])
+def test_c4_shape_1024_partitions_bit_exact(n):
+    """BASELINE config 4's per-GPU map side: 16 B key / 64 B value into 1024 partitions, compared byte for byte with the
+    oracle at sizes it still finishes in seconds (file.out, file.out.index, every partition's index triple)."""
+    import torch
+    kv = O.gen_c2(0, n, seed=11)
+    exp = O.pipelined_sort_fixed(O.sorter_conf(1024), kv, 16, 64)
+    with T.GpuSorter(1024, fixed=(16, 64)) as s:
+        d_kv = torch.from_numpy(kv).cuda()
+        cap = n * 82 + 10 * 1024 + 4096
+        d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        out_len, index, st = s.sort_device_fixed(d_kv.data_ptr(), n, d_out.data_ptr(), cap)
+        out = d_out[:out_len].cpu().numpy()
+    assert out_len == len(exp["file_out"])
+    assert np.array_equal(out, np.frombuffer(exp["file_out"], dtype=np.uint8)), "file.out differs from the oracle"
+    assert np.array_equal(index, exp["index"])
+    assert st["output_records"] == n and not st["rle_used"]
+
+
 def test_c2_fixed_multiple_collects_and_files(tmp_path):
     n, P = 30000, 7
     kv = O.gen_c2(100, n, seed=9)

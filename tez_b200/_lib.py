@@ -59,6 +59,7 @@ SYMBOLS = [
     ("tezgpu_debug_crc_emulate", C.c_uint32, [_V, C.c_uint64, C.c_uint32, C.c_uint32]),
     ("tezgpu_merge_open", C.c_int32, [_P(Conf), _P(Segment), C.c_uint32, _P(_V)]),
     ("tezgpu_merge_reopen", C.c_int32, [_V, _P(Segment), C.c_uint32]),
+    ("tezgpu_merge_set_check_for_same_keys", C.c_int32, [_V, C.c_int32]),
     ("tezgpu_merge_counts", C.c_int32, [_V, _P(C.c_uint64), _P(C.c_uint64)]),
     ("tezgpu_merge_next_batch", C.c_int32, [_V, _V, C.c_uint64, _P(KvIndex), C.c_uint32, _P(C.c_uint32)]),
     ("tezgpu_merge_write_ifile", C.c_int32, [_V, C.c_char_p, _V, C.c_uint64, C.c_int32, _P(C.c_int64), _P(C.c_int64), _P(Stats)]),
@@ -93,6 +94,7 @@ RT_SYMBOLS = [
     ("tezrt_input_initialize", C.c_int32, [_V, _P(C.c_int64)]),
     ("tezrt_input_start", C.c_int32, [_V]),
     ("tezrt_input_add_local_output", C.c_int32, [_V, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32]),
+    ("tezrt_input_add_local_spill", C.c_int32, [_V, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("tezrt_input_wait_ready", C.c_int32, [_V]),
     ("tezrt_input_next", C.c_int32, [_V, _P(_V), _P(C.c_uint32)]),
     ("tezrt_input_next_value", C.c_int32, [_V, _P(_V), _P(C.c_uint32)]),

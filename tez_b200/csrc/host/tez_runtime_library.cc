@@ -189,6 +189,8 @@ struct GpuSorter {
   std::vector<std::vector<int64_t>> spill_index;
   std::string final_out, final_index;
   std::vector<int64_t> final_idx;
+  std::vector<int64_t> partition_stats;  // partitionStats[p] += rawLength at every spill (SORT/PipelinedSorter.java:631-633)
+  int last_spill_rle = 0;                // merger.needsRLE() of the most recent spill's SpanMerger (:599,805,814)
   std::map<std::string, int64_t> &counters;
 
   GpuSorter(const tezgpu_conf &c, int64_t mem, bool fm, const std::string &wd, const std::string &u, std::map<std::string, int64_t> &ctr)
@@ -245,6 +247,9 @@ struct GpuSorter {
     else if (num_spills > 0) { counters["ADDITIONAL_SPILLS_BYTES_WRITTEN"] += st.file_out_bytes; counters["OUTPUT_BYTES_WITH_OVERHEAD"] = 0; }
     else counters["OUTPUT_BYTES_WITH_OVERHEAD"] += st.output_bytes_with_overhead;
     counters["SPILLED_RECORDS"] += st.spilled_records;
+    last_spill_rle = st.rle_used;
+    partition_stats.resize((size_t)P, 0);
+    for (int p = 0; p < P; p++) partition_stats[p] += idx[3 * p + 1];
     spill_files.push_back(f);
     spill_index_files.push_back(fi);
     spill_index.push_back(idx);
@@ -303,7 +308,11 @@ struct GpuSorter {
     gpu_check(tezgpu_merge_open(&mc, segs.data(), (uint32_t)segs.size(), &m));
     final_idx.assign((size_t)P * 3, 0);
     tezgpu_stats st;
-    int32_t rc = tezgpu_merge_write_partitions(m, final_out.c_str(), final_index.c_str(), /*rle=*/0, final_idx.data(), &st);
+    // TezMerger.merge(..., checkForSameKeys = merger.needsRLE()) into Writer(..., rle = merger.needsRLE()), `merger`
+    // being the SpanMerger of the last spill (SORT/PipelinedSorter.java:797-814)
+    int32_t rc = tezgpu_merge_set_check_for_same_keys(m, last_spill_rle);
+    if (rc == 0)
+      rc = tezgpu_merge_write_partitions(m, final_out.c_str(), final_index.c_str(), /*rle=*/last_spill_rle, final_idx.data(), &st);
     tezgpu_merge_close(m);
     gpu_check(rc);
     const uint64_t len = (uint64_t)st.file_out_bytes;
@@ -387,7 +396,10 @@ struct Output {
       pb_int(vm, 1, counters["OUTPUT_BYTES"]);
       std::string mode = conf.get(K_REPORT_STATS, "memory_optimized");
       std::vector<int64_t> sizes(P);
-      for (int p = 0; p < P; p++) sizes[p] = idx[3 * p + 1];
+      // without the final merge the event of the last spill reports the sizes accumulated over every spill
+      // (partitionStats, SORT/PipelinedSorter.java:631-633 -> ExternalSorter.getPartitionStats)
+      for (int p = 0; p < P; p++)
+        sizes[p] = (!final_merge && sorter && (int)sorter->partition_stats.size() == P) ? sorter->partition_stats[p] : idx[3 * p + 1];
       if (mode == "precise") {
         std::string d, packed;
         for (int p = 0; p < P; p++) pb_varint(packed, (uint64_t)((sizes[p] + (1 << 20) - 1) >> 20));
@@ -464,7 +476,11 @@ struct Input {
   bool initialized = false, started = false, ready = false;
   std::map<std::string, int64_t> counters;
   std::vector<std::vector<uint8_t>> seg_bytes;
-  std::vector<int> delivered;
+  // per source: spill ids seen and the id carried by the event with last_event_flag (pipelined shuffle; the reference's
+  // ShuffleScheduler tracks the same per input identifier: eventsProcessed / finalEventId, OG/ShuffleScheduler.java:540-600); spill id -1 = the single
+  // event of a producer that ran its final merge
+  struct SourceState { std::vector<int> spills; int last_id = -2; bool complete = false; };
+  std::vector<SourceState> delivered;
   int num_delivered = 0;
   tezgpu_merger *merger = nullptr;
   int cmp = 0;
@@ -476,7 +492,7 @@ struct Input {
   bool have_rec = false, eos = false, in_group = false, first_of_group = false;
 
   Input(const char *c, const char *wd, const char *u, int64_t mem, int n, int dev)
-      : conf(c), work_dir(wd ? wd : "."), uid(u ? u : "attempt"), N(n), device(dev), task_memory(mem), delivered(n, 0) {}
+      : conf(c), work_dir(wd ? wd : "."), uid(u ? u : "attempt"), N(n), device(dev), task_memory(mem), delivered(n) {}
   ~Input() { if (merger) tezgpu_merge_close(merger); }
 
   void initialize() {
@@ -491,12 +507,27 @@ struct Input {
     started = true;
     if (N == 0) ready = true;
   }
-  void add_local(int src, const char *file_out, const char *index_file, int partition, bool empty) {
+  void add_local(int src, const char *file_out, const char *index_file, int partition, bool empty, int spill_id, bool last_event) {
     RT_CHECK(started, TEZGPU_E_STATE, "handleEvents() before start()");
     RT_CHECK(src >= 0 && src < N, TEZGPU_E_INVALID, "source index out of range");
-    if (delivered[src]) return;  // duplicate event for an already fetched input
-    delivered[src] = 1;
-    num_delivered++;
+    RT_CHECK(spill_id >= -1, TEZGPU_E_INVALID, "bad spill id");
+    SourceState &ss = delivered[src];
+    if (spill_id < 0) {
+      if (ss.complete) return;  // duplicate event for an already fetched input
+      RT_CHECK(ss.spills.empty(), TEZGPU_E_STATE, "final-merge event for a source that already delivered spill events");
+      ss.complete = true;
+    } else {
+      RT_CHECK(!(ss.complete && ss.last_id == -2), TEZGPU_E_STATE, "spill event for a source that already delivered its final output");
+      for (int id : ss.spills) if (id == spill_id) return;  // duplicate spill event
+      RT_CHECK(ss.last_id == -2 || spill_id < ss.last_id, TEZGPU_E_INVALID, "spill id beyond the one flagged as last");
+      ss.spills.push_back(spill_id);
+      if (last_event) {
+        for (int id : ss.spills) RT_CHECK(id <= spill_id, TEZGPU_E_INVALID, "spill id beyond the one flagged as last");
+        ss.last_id = spill_id;
+      }
+      ss.complete = ss.last_id >= 0 && (int)ss.spills.size() == ss.last_id + 1;
+    }
+    if (ss.complete) num_delivered++;
     if (empty) { counters["NUM_SKIPPED_INPUTS"]++; return; }
     // TezSpillRecord(indexFile): P x 3 big-endian longs + checksum (SORT/TezSpillRecord.java:76-109)
     std::vector<uint8_t> ib = read_file(index_file);
@@ -641,7 +672,11 @@ int32_t tezrt_input_create(const char *conf, const char *work_dir, const char *u
 int32_t tezrt_input_initialize(tezrt_input *in, int64_t *requested) { RT_BEGIN in->i.initialize(); if (requested) *requested = in->i.requested; RT_END }
 int32_t tezrt_input_start(tezrt_input *in) { RT_BEGIN in->i.start(); RT_END }
 int32_t tezrt_input_add_local_output(tezrt_input *in, int32_t src, const char *file_out, const char *index_file, int32_t partition, int32_t empty) {
-  RT_BEGIN in->i.add_local(src, file_out, index_file, partition, empty != 0); RT_END
+  RT_BEGIN in->i.add_local(src, file_out, index_file, partition, empty != 0, -1, true); RT_END
+}
+int32_t tezrt_input_add_local_spill(tezrt_input *in, int32_t src, const char *file_out, const char *index_file, int32_t partition, int32_t empty,
+                                    int32_t spill_id, int32_t last_event) {
+  RT_BEGIN in->i.add_local(src, file_out, index_file, partition, empty != 0, spill_id, last_event != 0); RT_END
 }
 int32_t tezrt_input_wait_ready(tezrt_input *in) { RT_BEGIN in->i.wait_ready(); RT_END }
 int32_t tezrt_input_next(tezrt_input *in, const uint8_t **key, uint32_t *klen) {

@@ -344,7 +344,7 @@ struct KvIndexDev { uint32_t key_off, key_len, val_off, val_len, same_key; };
 __global__ void __launch_bounds__(256)
     k_gather_batch(Records rec, const uint32_t *__restrict__ order, const uint8_t *__restrict__ same,
                    const uint64_t *__restrict__ kv_off, uint32_t cursor, uint32_t count, uint8_t *__restrict__ out,
-                   KvIndexDev *__restrict__ idx) {
+                   KvIndexDev *__restrict__ idx, int check_same) {
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= count) return;
   const uint32_t r = cursor + w, i = order[r];
@@ -357,11 +357,12 @@ __global__ void __launch_bounds__(256)
   if (lane == 0) {
     KvIndexDev e;
     e.key_off = (uint32_t)o; e.key_len = kl; e.val_off = (uint32_t)(o + kl); e.val_len = vl;
-    // MergeQueue.isSameKey(): read as SAME_KEY from its segment, or equal to the previous key of another segment
+    // MergeQueue.isSameKey(): read as SAME_KEY from its segment, or (checkForSameKeys) equal to the previous key of
+    // another segment
     bool sk = false;
     if (r > 0 && same[r]) {
       const uint32_t tag = rec.tag[i], tagp = rec.tag[order[r - 1]];
-      sk = (tag & 1u) || ((tag >> 1) != (tagp >> 1));
+      sk = (tag & 1u) || (check_same && ((tag >> 1) != (tagp >> 1)));
     }
     e.same_key = sk ? 1u : 0u;
     idx[w] = e;
@@ -566,6 +567,7 @@ class Merger {
       r.klen = fixed_klen;
       r.vlen = fixed_vlen;
     }
+    pipe.merge_inputs_plain = parsed_fixed;
     pipe.sort_phase(r);
     launches += pipe.state.launches;
     cursor = 0;
@@ -601,6 +603,8 @@ class Merger {
 
   // TezMerger.writeFile: one IFile segment, equal adjacent keys written through IFile.REPEAT_KEY
   void write_device(uint8_t *d_out_buf, uint64_t cap, int writer_rle, int64_t *raw_len, int64_t *part_len, tezgpu_stats *stats) {
+    TG_CHECK(pipe.conf.num_partitions == 1, TEZGPU_E_STATE,
+             "merger was opened with num_partitions > 1: use tezgpu_merge_write_partitions*");
     int64_t index[3] = {0, 0, 0};
     uint64_t len = 0;
     tezgpu_stats st;
@@ -663,7 +667,8 @@ class Merger {
     d_batch_idx.ensure((size_t)cnt * sizeof(KvIndexDev));
     k_gather_batch<<<(uint32_t)div_up((uint64_t)cnt * 32, 256), 256, 0, st>>>(pipe.state.rec, pipe.state.order, pipe.same.as<uint8_t>(),
                                                                          d_kvoff.as<uint64_t>(), (uint32_t)cursor, cnt,
-                                                                         d_batch.as<uint8_t>(), d_batch_idx.as<KvIndexDev>());
+                                                                         d_batch.as<uint8_t>(), d_batch_idx.as<KvIndexDev>(),
+                                                                         pipe.merge_check_same);
     TG_CUDA(cudaGetLastError());
     if (bytes) TG_CUDA(cudaMemcpyAsync(out_kv, d_batch.p, bytes, cudaMemcpyDeviceToHost, st));
     static_assert(sizeof(KvIndexDev) == sizeof(tezgpu_kv_index), "index layout");

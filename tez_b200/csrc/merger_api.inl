@@ -34,6 +34,13 @@ int32_t tezgpu_merge_reopen(tezgpu_merger *m, const tezgpu_segment *segs, uint32
   TG_API_END
 }
 
+int32_t tezgpu_merge_set_check_for_same_keys(tezgpu_merger *m, int32_t check_for_same_keys) {
+  TG_API_BEGIN
+  TG_CHECK(m, TEZGPU_E_INVALID, "null handle");
+  m->m.pipe.merge_check_same = check_for_same_keys ? 1 : 0;
+  TG_API_END
+}
+
 int32_t tezgpu_merge_counts(tezgpu_merger *m, uint64_t *records, uint64_t *kv_bytes) {
   TG_API_BEGIN
   TG_CHECK(m, TEZGPU_E_INVALID, "null handle");

@@ -21,6 +21,7 @@ constexpr uint64_t FETCH_CHUNK = (uint64_t)FETCH_THREADS * FETCH_UNROLL * 16 * 2
 
 // the producer rewrites its buffer every step: never serve a peer byte from a local cache line (ld.cv)
 __device__ __forceinline__ uint4 ld_peer_16(const uint4 *p) { return __ldcv(p); }
+__device__ __forceinline__ uint8_t ld_peer_8(const uint8_t *p) { return __ldcv(p); }  // head / tail / misaligned bytes: same rule
 
 __device__ __forceinline__ void fetch_ranges_body(const FetchRange *__restrict__ ranges, uint32_t nranges, uint64_t nchunks) {
   for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -34,7 +35,7 @@ __device__ __forceinline__ void fetch_ranges_body(const FetchRange *__restrict__
     const uint32_t mis = (uint32_t)((uintptr_t)r.src & 15u);
     if (mis != (uint32_t)((uintptr_t)r.dst & 15u)) {  // incompatible alignment: bytes
       const uint64_t a = k * FETCH_CHUNK, b = min(r.len, a + FETCH_CHUNK);
-      for (uint64_t i = a + threadIdx.x; i < b; i += FETCH_THREADS) r.dst[i] = r.src[i];
+      for (uint64_t i = a + threadIdx.x; i < b; i += FETCH_THREADS) r.dst[i] = ld_peer_8(r.src + i);
       continue;
     }
     // body: the 16-byte words between the first and the last aligned address of the range
@@ -54,9 +55,9 @@ __device__ __forceinline__ void fetch_ranges_body(const FetchRange *__restrict__
     for (; i < w1; i += FETCH_THREADS) d16[i] = ld_peer_16(s16 + i);
     if (k == 0) {  // the unaligned head and tail bytes of the range travel with its first chunk
       const uint64_t tail0 = head + (words << 4);
-      if (threadIdx.x < head) r.dst[threadIdx.x] = r.src[threadIdx.x];
+      if (threadIdx.x < head) r.dst[threadIdx.x] = ld_peer_8(r.src + threadIdx.x);
       if (threadIdx.x >= 32 && tail0 + (threadIdx.x - 32) < r.len && threadIdx.x - 32 < 16)
-        r.dst[tail0 + (threadIdx.x - 32)] = r.src[tail0 + (threadIdx.x - 32)];
+        r.dst[tail0 + (threadIdx.x - 32)] = ld_peer_8(r.src + tail0 + (threadIdx.x - 32));
     }
   }
 }

@@ -112,6 +112,10 @@ class SortPipeline {
     bool have_bounds = false, spec_layout = false;  // partition bounds / fixed-width layout already on the device
     uint64_t spec_file_bytes = 0, spec_tiles = 0;
   } state;
+  // merge mode only (the Merger sets them): MergeQueue.checkForSameKeys, and "no input record was run-length encoded"
+  // (every segment had the plain fixed framing), which together decide whether any record can be written as a repeat
+  int merge_check_same = 1;
+  bool merge_inputs_plain = false;
 
   EmitParams make_emit_params(const Records &rec, const uint32_t *order, int rle, bool merge_mode, uint8_t *d_out) {
     EmitParams e;
@@ -128,6 +132,7 @@ class SortPipeline {
     e.rle = rle;
     e.send_empty = conf.send_empty_partition_details;
     e.merge_mode = merge_mode ? 1 : 0;
+    e.check_same = merge_check_same;
     e.P = conf.num_partitions;
     return e;
   }
@@ -379,7 +384,9 @@ class SortPipeline {
       launches++;
     }
     // constant-size framing is only valid when no record is written as a repeat (merge mode flags repeats on its own)
-    const bool fixed_emit = rec.fixed && (dup_count == 0 || (!rle && !merge_mode));
+    // (a merge writes repeats for isSameKey() records: none exist when checkForSameKeys is off and no input was encoded)
+    const bool no_repeats = !rle && (!merge_mode || (!merge_check_same && merge_inputs_plain));
+    const bool fixed_emit = rec.fixed && (dup_count == 0 || no_repeats);
     uint64_t bound = output_bound(n, rec.fixed ? (uint64_t)n * (rec.klen + rec.vlen) : rec.kv_bytes, P);
     uint64_t *hs = h_small.as<uint64_t>();
     if (fixed_emit && state.spec_layout) {

@@ -198,102 +198,7 @@ __global__ void __launch_bounds__(SCAN_THREADS)
   }
 }
 
-// Single-pass version of k_tie_count + scan + k_tie_compact: chained scan with decoupled look-back over the tiles
-// (state = flag:2 | heads:31 | tied:31), so the sort words are read once and no host round trip is needed.
-// *m_out receives the number of tied records.
-constexpr uint64_t TIE_FLAG_AGG = 1ull << 62, TIE_FLAG_INCL = 2ull << 62, TIE_VAL_MASK = (1ull << 62) - 1;
-
-__global__ void __launch_bounds__(SCAN_THREADS)
-    k_tie_scan(const uint32_t *__restrict__ K, const uint32_t *__restrict__ order, uint32_t n, uint64_t *state,
-               uint32_t *ticket, uint32_t *__restrict__ pos, uint32_t *__restrict__ gid, uint32_t *__restrict__ lidx,
-               uint32_t *__restrict__ m_out) {
-  __shared__ uint32_t s_k[SCAN_TILE + 2];
-  __shared__ uint32_t s_ct[SCAN_IPT][SCAN_THREADS / 32], s_ch[SCAN_IPT][SCAN_THREADS / 32];
-  __shared__ uint64_t s_base;
-#ifdef TEZGPU_TICKET_ATOMIC
-  __shared__ uint32_t s_tile;
-  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-  __syncthreads();
-  const uint32_t tile = s_tile;
-#else
-  (void)ticket;
-  const uint32_t tile = blockIdx.x;  // in-order dispatch of a 1-D grid (see radix_sort.cuh)
-#endif
-  TileFlags f;
-  tile_load_flags(K, n, s_k, f, tile);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t lt = lanemask_lt();
-  uint32_t bt[SCAN_IPT], bh[SCAN_IPT];
-#pragma unroll
-  for (int k = 0; k < SCAN_IPT; k++) {
-    bt[k] = __ballot_sync(0xffffffffu, f.t[k]);
-    bh[k] = __ballot_sync(0xffffffffu, f.h[k]);
-    if (lane == 0) { s_ct[k][warp] = __popc(bt[k]); s_ch[k][warp] = __popc(bh[k]); }
-  }
-  __syncthreads();
-  if (warp == 0) {
-    // block aggregate, then a warp-wide decoupled look-back: lane l inspects tile (t - l), so 32 predecessors cost one
-    // round trip instead of 32
-    uint32_t at = 0, ah = 0;
-    for (int q = lane; q < SCAN_IPT * (SCAN_THREADS / 32); q += 32) { at += (&s_ct[0][0])[q]; ah += (&s_ch[0][0])[q]; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { at += __shfl_xor_sync(0xffffffffu, at, o); ah += __shfl_xor_sync(0xffffffffu, ah, o); }
-    const uint64_t agg = (uint64_t)at | ((uint64_t)ah << 31);
-    uint64_t excl = 0;
-    if (tile == 0) {
-      if (lane == 0) st_volatile_u64(&state[0], TIE_FLAG_INCL | agg);
-    } else {
-      if (lane == 0) st_volatile_u64(&state[tile], TIE_FLAG_AGG | agg);
-      int64_t t = (int64_t)tile - 1;
-      while (true) {
-        const int64_t mine = t - lane;
-        uint64_t sv = mine >= 0 ? ld_volatile_u64(&state[mine]) : TIE_FLAG_INCL;  // before tile 0: inclusive zero
-        const uint64_t flag = sv & ~TIE_VAL_MASK;
-        const uint32_t ready = __ballot_sync(0xffffffffu, flag != 0);
-        const uint32_t incl = __ballot_sync(0xffffffffu, flag == TIE_FLAG_INCL);
-        // usable prefix of the window: lanes 0..k-1 all published, stop at the first inclusive one
-        const uint32_t first_unready = ready == 0xffffffffu ? 32u : (uint32_t)__ffs(~ready) - 1u;
-        const uint32_t first_incl = incl ? (uint32_t)__ffs(incl) - 1u : 32u;
-        const uint32_t take = first_incl < first_unready ? first_incl + 1u : first_unready;  // lanes [0, take)
-        uint64_t v = (uint32_t)lane < take ? (sv & TIE_VAL_MASK) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        excl += v;
-        t -= take;
-        if (first_incl < first_unready) break;
-      }
-      if (lane == 0) st_volatile_u64(&state[tile], TIE_FLAG_INCL | (excl + agg));
-    }
-    if (lane == 0) {
-      s_base = excl;
-      if ((uint64_t)(tile + 1) * SCAN_TILE >= n) *m_out = (uint32_t)((excl + agg) & 0x7FFFFFFFull);
-    }
-  }
-  __syncthreads();
-  const uint64_t b0 = s_base;
-  uint32_t run_t = (uint32_t)(b0 & 0x7FFFFFFFull), run_h = (uint32_t)(b0 >> 31);
-  const uint32_t base = tile * SCAN_TILE;
-#pragma unroll
-  for (int k = 0; k < SCAN_IPT; k++) {
-    uint32_t pre_t = run_t, pre_h = run_h;
-#pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; w++) {
-      uint32_t ct = s_ct[k][w], ch = s_ch[k][w];
-      if (w < warp) { pre_t += ct; pre_h += ch; }
-      run_t += ct; run_h += ch;
-    }
-    if (f.t[k]) {
-      uint32_t at = pre_t + __popc(bt[k] & lt);
-      uint32_t heads = pre_h + __popc(bh[k] & lt) + (f.h[k] ? 1u : 0u);
-      uint32_t i = base + k * SCAN_THREADS + threadIdx.x;
-      pos[at] = i;
-      gid[at] = heads - 1;
-      lidx[at] = order[i];
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ small tie groups
+// ------------------------------------------------------------------------------------------------ key comparison
 // full RawComparator order of two records' keys from normalised content byte `depth` on (bytes before it are equal)
 __device__ __forceinline__ int compare_keys_from(const Records &r, uint32_t ra, uint32_t rb, uint32_t depth) {
   uint64_t ka, kb;
@@ -312,52 +217,6 @@ __device__ __forceinline__ int compare_keys_from(const Records &r, uint32_t ra, 
 }
 
 constexpr uint32_t TIE_SMALL_MAX = 16;
-
-// One thread per tied record: groups of at most TIE_SMALL_MAX records are ordered directly with the full comparator
-// (rank = #smaller + #equal-and-earlier).  With uniformly distributed keys almost every group has 2-3 members.
-// Larger groups are only counted; the host then runs the radix refinement rounds.
-__device__ __forceinline__ void tie_small_one(const Records &r, const uint32_t *__restrict__ pos, const uint32_t *__restrict__ gid,
-                                              const uint32_t *__restrict__ lidx, uint32_t m, uint32_t j, uint32_t depth,
-                                              uint32_t *__restrict__ order, uint8_t *__restrict__ same,
-                                              unsigned long long *__restrict__ dup_count, uint32_t *__restrict__ large_groups) {
-  const uint32_t g = gid[j];
-  uint32_t s = j;
-  while (s > 0 && gid[s - 1] == g && j - s < TIE_SMALL_MAX) s--;
-  bool large = (s > 0 && gid[s - 1] == g);
-  uint32_t e = j + 1;
-  if (!large) {
-    while (e < m && gid[e] == g && e - s <= TIE_SMALL_MAX) e++;
-    large = (e - s > TIE_SMALL_MAX);
-  }
-  if (large) {
-    if (j == 0 || gid[j - 1] != g) atomicAdd(large_groups, 1u);
-    return;
-  }
-  const uint32_t me = lidx[j];
-  uint32_t rank = 0, eq_before = 0;
-  for (uint32_t q = s; q < e; q++) {
-    if (q == j) continue;
-    int c = compare_keys_from(r, lidx[q], me, depth);
-    if (c < 0) rank++;
-    else if (c == 0 && q < j) { rank++; eq_before++; }
-  }
-  const uint32_t p = pos[s + rank];
-  order[p] = me;
-  if (eq_before) {
-    same[p] = 1;  // byte-identical to the key at sorted position p-1
-    atomicAdd(dup_count, 1ull);
-  }
-}
-
-__global__ void __launch_bounds__(256)
-    k_tie_small(Records r, const uint32_t *__restrict__ pos, const uint32_t *__restrict__ gid,
-                const uint32_t *__restrict__ lidx, const uint32_t *__restrict__ m_ptr, uint32_t depth,
-                uint32_t *__restrict__ order, uint8_t *__restrict__ same, unsigned long long *__restrict__ dup_count,
-                uint32_t *__restrict__ large_groups) {
-  const uint32_t m = *m_ptr;
-  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x)
-    tie_small_one(r, pos, gid, lidx, m, j, depth, order, same, dup_count, large_groups);
-}
 
 // ------------------------------------------------------------------------------------------------ in-place tie fix
 // One streaming pass over the sorted sort words finds the head of every group of colliding records; groups of at most
@@ -426,6 +285,9 @@ __global__ void __launch_bounds__(TIEFIX_THREADS)
     __syncthreads();
     const uint32_t nh = s_nheads;
     const bool last = tile + gridDim.x >= ntiles;
+    // every thread has read nh before any thread of the next iteration bumps s_nheads again (the flush decision must be
+    // CTA-uniform: the branches below contain barriers)
+    __syncthreads();
     if (nh >= (uint32_t)TIEFIX_FLUSH || last) {
       for (uint32_t hidx = threadIdx.x; hidx < nh; hidx += TIEFIX_THREADS)
         tie_fix_group(r, K, order, n, s_heads[hidx], depth, same, my_dups, my_ties, large_groups);
@@ -579,6 +441,7 @@ struct EmitParams {
   uint32_t fixed_hdr_len;
   int rle;
   int merge_mode;      // TezMerger.writeFile semantics: isSameKey() records go through IFile.REPEAT_KEY
+  int check_same;      // merge_mode: MergeQueue.checkForSameKeys (SORT/TezMerger.java:563-573,597-652)
   int send_empty;
   int P;
 };
@@ -598,8 +461,11 @@ __device__ __forceinline__ bool emit_is_repeat(const EmitParams &e, uint32_t r, 
   record_lookup(rec, i, koff, klen, vlen);
   const bool writer = e.rle && klen > 0;
   if (!e.merge_mode) return writer;
-  const uint32_t tag = rec.tag[i], tagp = rec.tag[e.order[r - 1]];
-  return writer || (tag & 1u) || ((tag >> 1) != (tagp >> 1));
+  // read as SAME_KEY from its own segment; with checkForSameKeys also "the top segment changed and its key equals the
+  // previous key" (compareKeyWithNextTopKey, :640-652)
+  const uint32_t tag = rec.tag[i];
+  if (writer || (tag & 1u)) return true;
+  return e.check_same && ((tag >> 1) != (rec.tag[e.order[r - 1]] >> 1));
 }
 
 // var mode: emitted size of the record at sorted position r (IFile.Writer.writeKVPair / writeValue / markers,

@@ -170,6 +170,10 @@ class GpuMerger:
     def __exit__(self, *a):
         self.close()
 
+    def set_check_for_same_keys(self, on):
+        """MergeQueue's checkForSameKeys (SORT/TezMerger.java:560-573); default True."""
+        check(self.L.tezgpu_merge_set_check_for_same_keys(self.h, 1 if on else 0))
+
     def counts(self):
         r, b = C.c_uint64(), C.c_uint64()
         check(self.L.tezgpu_merge_counts(self.h, C.byref(r), C.byref(b)))

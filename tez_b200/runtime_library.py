@@ -182,6 +182,8 @@ class LocalOutput:
     index_file: str
     partition: int
     empty: bool = False
+    spill_id: int = -1          # >= 0: event of one spill of a producer without final merge (pipelined shuffle)
+    last_event: bool = False
 
 
 class KeyValuesReader:
@@ -233,8 +235,14 @@ class OrderedGroupedKVInput:
 
     def handleEvents(self, local_outputs):
         for lo in local_outputs:
-            check_rt(self._L.tezrt_input_add_local_output(self._h, lo.source_index, lo.file_out.encode(),
-                                                          lo.index_file.encode(), lo.partition, 1 if lo.empty else 0))
+            spill_id = getattr(lo, "spill_id", -1)
+            if spill_id is None or spill_id < 0:
+                check_rt(self._L.tezrt_input_add_local_output(self._h, lo.source_index, lo.file_out.encode(),
+                                                              lo.index_file.encode(), lo.partition, 1 if lo.empty else 0))
+            else:   # pipelined shuffle: one event per spill of the producer
+                check_rt(self._L.tezrt_input_add_local_spill(self._h, lo.source_index, lo.file_out.encode(),
+                                                             lo.index_file.encode(), lo.partition, 1 if lo.empty else 0,
+                                                             spill_id, 1 if getattr(lo, "last_event", False) else 0))
 
     def waitForInputReady(self):
         check_rt(self._L.tezrt_input_wait_ready(self._h))
