@@ -144,6 +144,9 @@ void *tezgpu_sorter_stream(tezgpu_sorter *h);
  * ---------------------------------------------------------------------------------------------------------------- */
 #define TEZGPU_SEG_HAS_HEADER 1u   /* on-disk layout: 'T','I','F',flag + body + crc  (DiskSegment); else body + crc (InMemoryReader) */
 #define TEZGPU_SEG_DEVICE 2u       /* data is a device pointer on conf.device */
+#define TEZGPU_SEG_VERIFIED 4u     /* the transport already verified this segment's checksum while copying it (as
+                                      IFile.Reader.readToMemory does for fetched MEMORY outputs, SORT/IFile.java:764-809,
+                                      whose InMemoryReader then never re-checks): tezgpu_fetch_segments_verified */
 
 typedef struct tezgpu_segment {
   const void *data;
@@ -217,6 +220,22 @@ typedef struct tezgpu_copy_range {
  * the bytes have landed */
 int32_t tezgpu_fetch_ranges(int32_t device, const tezgpu_copy_range *ranges, uint32_t n, void *stream,
                             float *ms_kernel);
+
+/* The same pull with every segment's IFile checksum verified on the bytes as they pass through the copy kernel -- what
+ * IFile.Reader.readToMemory does when FetcherOrderedGrouped fetches a map output to MEMORY (SORT/IFile.java:764-809,
+ * OG/FetcherOrderedGrouped.java:519-533).  One entry per (non-empty) segment; src may be a peer mapping, dst is local,
+ * (dst - src) must be a multiple of 16 and only the bytes of the listed segments move.  Fails with TEZGPU_E_FORMAT
+ * ("IFile checksum mismatch in fetched segment i") like the reference's ChecksumException; segments that passed may be
+ * handed to tezgpu_merge_open with TEZGPU_SEG_VERIFIED so the merge does not read them a second time to check. */
+typedef struct tezgpu_fetch_segment {
+  const void *src;
+  void *dst;
+  uint64_t len;                    /* whole segment: header + body + 4 checksum bytes */
+  uint32_t flags;                  /* TEZGPU_SEG_HAS_HEADER */
+  uint32_t reserved;
+} tezgpu_fetch_segment;
+int32_t tezgpu_fetch_segments_verified(int32_t device, const tezgpu_fetch_segment *segs, uint32_t n, void *stream,
+                                       float *ms_kernel);
 
 /* diagnostics: host-side emulation of the device's tiled CRC algebra (same tables, no GPU needed) */
 uint32_t tezgpu_debug_crc_emulate(const uint8_t *body, uint64_t len, uint32_t piece_bytes, uint32_t lead);

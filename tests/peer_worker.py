@@ -34,9 +34,10 @@ def main():
         parts = [p for _, _, p, _ in segs]
         if merger is None:
             merger = T.GpuMerger(seg_list, comparator=T.CMP_BYTES, device_ptrs=True, fixed=(16, 64), partitions=parts,
-                                 num_partitions=max(1, p1 - p0))
+                                 num_partitions=max(1, p1 - p0), verified=px.last_verified)
         else:
-            merger.reopen(seg_list, parts)
+            merger.reopen(seg_list, parts, verified=px.last_verified)
+        assert px.last_verified is not None and sum(px.last_verified) == sum(1 for _, _, _, g in segs if g != rank)
         d_merged = torch.empty(merger.output_bound() + 64, dtype=torch.uint8, device=dev)
         mlen, mindex, _ = merger.write_partitions_device(d_merged.data_ptr(), d_merged.numel())
         got = d_merged[:mlen].cpu().numpy().tobytes()

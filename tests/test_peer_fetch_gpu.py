@@ -40,6 +40,48 @@ def test_fetch_ranges_every_alignment_and_size():
     assert np.array_equal(h_dst, want)   # ranges landed, guard bytes and gaps untouched
 
 
+def test_fetch_segments_verified_copies_and_checks_every_segment():
+    """The pull with the IFile CRC32 verified in flight (IFile.Reader.readToMemory semantics, SORT/IFile.java:764-809):
+    segments of every size class (empty, shorter than a word, one piece, many 64 KiB pieces) at every alignment."""
+    import random
+    import zlib
+    from oracle import tez_oracle as O
+    rng = random.Random(12)
+    segs = [O.write_ifile([])[0]]
+    for nrec in (1, 2, 7, 100, 3000, 40000):
+        recs = sorted((rng.getrandbits(64).to_bytes(8, "big"), rng.randbytes(rng.randint(0, 40))) for _ in range(nrec))
+        segs.append(O.write_ifile(recs, rle=False)[0])
+    inmem = [s[4:] for s in segs[1:4]]                      # header-less (InMemoryWriter) segments: body + crc
+    dev = torch.device("cuda", 0)
+    for has_header, group in ((True, segs), (False, inmem)):
+        for lead in (0, 1, 4, 7, 12, 15):
+            blob = bytearray(b"\xAA" * lead)
+            offs = []
+            for s_ in group:
+                offs.append(len(blob))
+                blob += s_                                    # back to back like a file.out range
+            src = torch.frombuffer(bytes(blob) + b"\xBB" * 64, dtype=torch.uint8).to(dev)
+            dst = torch.full((len(blob) + 64 + 32,), 0xCC, dtype=torch.uint8, device=dev)
+            d0 = 16                                           # same residue modulo 16 as the source (both 256-aligned bases)
+            table = [(src.data_ptr() + o, dst.data_ptr() + d0 + o, len(s_)) for o, s_ in zip(offs, group)]
+            ms = T.fetch_segments_verified(table, has_header=has_header)
+            assert ms >= 0
+            got = dst.cpu().numpy()
+            want = np.full(len(got), 0xCC, dtype=np.uint8)
+            want[d0 + lead:d0 + len(blob)] = np.frombuffer(bytes(blob[lead:]), dtype=np.uint8)
+            assert np.array_equal(got, want), (has_header, lead)   # segments landed, nothing around them was touched
+    # a flipped bit anywhere (body, last partial word, trailer) is a checksum error naming the segment
+    big = segs[-1]
+    for pos in (4, len(big) // 2, len(big) - 6, len(big) - 1):
+        bad = bytearray(big)
+        bad[pos] ^= 0x10
+        src = torch.frombuffer(bytes(segs[2]) + bytes(bad), dtype=torch.uint8).to(dev)
+        dst = torch.zeros(src.numel() + 16, dtype=torch.uint8, device=dev)
+        table = [(src.data_ptr(), dst.data_ptr(), len(segs[2])), (src.data_ptr() + len(segs[2]), dst.data_ptr() + len(segs[2]), len(bad))]
+        with pytest.raises(IOError, match="checksum mismatch in fetched segment 1"):
+            T.fetch_segments_verified(table)
+
+
 @pytest.mark.parametrize("world,n,P", [(2, 20000, 8), (3, 5000, 7)])
 def test_sort_pull_merge_across_processes(world, n, P):
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")

@@ -73,6 +73,7 @@ SYMBOLS = [
     ("tezgpu_peer_open", C.c_int32, [C.c_int32, _V, _P(_V)]),
     ("tezgpu_peer_close", C.c_int32, [C.c_int32, _V]),
     ("tezgpu_fetch_ranges", C.c_int32, [C.c_int32, _P(CopyRange), C.c_uint32, _V, _P(C.c_float)]),
+    ("tezgpu_fetch_segments_verified", C.c_int32, [C.c_int32, _V, C.c_uint32, _V, _P(C.c_float)]),
     ("tezgpu_merge_close", C.c_int32, [_V]),
 ]
 

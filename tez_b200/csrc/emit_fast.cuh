@@ -135,6 +135,15 @@ struct FastEmitParams {
   uint32_t stride;
 };
 
+// byte offset in kv of record ri's key: explicit array, arithmetic over the run table, or packed
+__device__ __forceinline__ uint64_t fast_source_offset(const Records &rec, uint32_t ri, uint32_t stride) {
+  if (rec.use_runs) {
+    uint32_t seg;
+    return run_record_off(rec.runs, ri, seg) + rec.runs.hdr_len;
+  }
+  return rec.key_off ? rec.key_off[ri] : (uint64_t)ri * stride;
+}
+
 #ifndef TEZGPU_CRC_SHFL
 #define TEZGPU_CRC_SHFL 1
 #endif
@@ -181,7 +190,7 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT_MIN_CTAS) k_emit_fast(
     if ((uint32_t)tid < td_next.nr) {
       const uint32_t ri = e.order[td_next.r0 + tid];
       s_idx[0][tid] = ri;
-      if (!ALIGNED) s_off[0][tid] = e.rec.key_off ? e.rec.key_off[ri] : (uint64_t)ri * stride;
+      if (!ALIGNED) s_off[0][tid] = fast_source_offset(e.rec, ri, stride);
     }
   }
   uint32_t buf = 0;
@@ -248,7 +257,7 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT_MIN_CTAS) k_emit_fast(
     if (tile_n < fp.ntiles && (uint32_t)tid < td_next.nr) {
       const uint32_t ri = e.order[td_next.r0 + tid];
       s_idx[buf ^ 1u][tid] = ri;
-      if (!ALIGNED) s_off[buf ^ 1u][tid] = e.rec.key_off ? e.rec.key_off[ri] : (uint64_t)ri * stride;
+      if (!ALIGNED) s_off[buf ^ 1u][tid] = fast_source_offset(e.rec, ri, stride);
     }
     // ---- framing: vint(klen) vint(vlen) in front of every record, segment header, EOF markers
     if ((uint32_t)tid < nr) {

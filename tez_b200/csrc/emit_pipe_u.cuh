@@ -72,7 +72,14 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast
   const uint64_t *__restrict__ key_off = e.rec.key_off;
   const uint32_t rec_size = e.rec_size, hdr_len = e.fixed_hdr_len, stride = fp.stride, cpr = fp.cpr;
   const TileDesc *__restrict__ tiles = fp.tiles;
-  auto source_offset = [&](uint32_t ri) -> uint64_t { return key_off ? key_off[ri] : (uint64_t)ri * stride; };
+  const bool use_runs = e.rec.use_runs;
+  auto source_offset = [&](uint32_t ri) -> uint64_t {
+    if (use_runs) {  // fixed-framing runs read in place: offset = f(segment table, index), no per-record array
+      uint32_t seg;
+      return run_record_off(e.rec.runs, ri, seg) + e.rec.runs.hdr_len;
+    }
+    return key_off ? key_off[ri] : (uint64_t)ri * stride;
+  };
 
   // lane <-> (record slot of the warp, aligned word k of that record); leftover lanes idle
   const uint32_t wpr = cpr + 1, rpw = 32u / wpr;                 // words per record, records per warp and round

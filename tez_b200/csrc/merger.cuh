@@ -16,7 +16,7 @@ struct SegDesc {
   uint64_t len;       // total bytes
   uint64_t body0;     // offset of the first body byte inside the segment (4 with header, 0 in-memory)
   uint64_t body_end;  // offset just past the EOF markers' possible position: len - 4 (checksum / slack excluded)
-  uint32_t has_header;
+  uint32_t has_header;  // bit 0: 'TIF' header present; bit 1: checksum already verified by the transport (skip)
   uint32_t partition;
 };
 
@@ -116,7 +116,7 @@ __global__ void k_check_headers(const uint8_t *__restrict__ data, const SegDesc 
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nseg) return;
   const SegDesc sd = segs[s];
-  if (!sd.has_header) return;
+  if (!(sd.has_header & 1u)) return;
   const uint8_t *h = data + sd.off;
   if (!(h[0] == 'T' && h[1] == 'I' && h[2] == 'F')) atomicExch(bad_magic, (int)s + 1);
   else if (h[3] != 0) atomicExch(compressed, (int)s + 1);
@@ -128,7 +128,9 @@ __global__ void k_crc_check(const uint8_t *__restrict__ data, const SegDesc *__r
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nseg) return;
   const SegDesc sd = segs[s];
-  if (!sd.has_header) return;  // in-memory segments carry no checksum stream (OG/InMemoryReader.java:142-254)
+  // in-memory segments carry no checksum stream (OG/InMemoryReader.java:142-254); segments the transport verified
+  // while copying them (IFile.Reader.readToMemory, SORT/IFile.java:764-809) are not verified twice
+  if (sd.has_header != 1u) return;
   const uint64_t body = sd.body_end - sd.body0;
   uint32_t crc = seg_crc[s] ^ crc_shift_bytes(t, 0xFFFFFFFFu, body) ^ 0xFFFFFFFFu;
   const uint8_t *tr = data + sd.off + sd.body_end;
@@ -289,12 +291,10 @@ __global__ void __launch_bounds__(PARSE_WARPS * 32)
   }
 }
 
-// fixed-width shortcut (multi-GPU shuffle of device-sorted partitions): when the body is exactly n records of a
-// known framing and every record position carries that framing, the sequential walk would visit exactly these
-// positions, so the metadata is pure arithmetic.  ok[s] = 0 if any position disagrees.
-__global__ void k_parse_fixed_check(const uint8_t *__restrict__ data, const SegDesc *__restrict__ segs, uint32_t nseg,
-                                    const uint64_t *__restrict__ rec_base, uint32_t klen, uint32_t vlen, uint32_t hdr_len,
-                                    uint64_t hdr_bytes /*packed little-endian*/, ParseArrays out, int *__restrict__ mismatch) {
+// run-table mode -> explicit arrays (only when the record iterator or the run-length encoding emit needs them):
+// every body is exactly n records of a known framing (checked by k_stage), so the metadata is pure arithmetic
+__global__ void k_fill_fixed_arrays(const SegDesc *__restrict__ segs, uint32_t nseg, const uint64_t *__restrict__ rec_base,
+                                    uint32_t klen, uint32_t vlen, uint32_t hdr_len, ParseArrays out) {
   const uint64_t total = rec_base[nseg];
   const uint32_t rs = hdr_len + klen + vlen;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -305,9 +305,6 @@ __global__ void k_parse_fixed_check(const uint8_t *__restrict__ data, const SegD
     }
     const SegDesc sd = segs[lo];
     const uint64_t pos = sd.off + sd.body0 + (i - rec_base[lo]) * rs;
-    bool ok = true;
-    for (uint32_t b = 0; b < hdr_len; b++) ok &= data[pos + b] == (uint8_t)(hdr_bytes >> (8 * b));
-    if (!ok) *mismatch = 1;
     out.key_off[i] = pos + hdr_len;
     out.val_off[i] = pos + hdr_len + klen;
     out.key_len[i] = klen;
@@ -395,10 +392,15 @@ class Merger {
 
   explicit Merger(const tezgpu_conf &c) : pipe(pipe_conf(c)), fixed_klen(c.fixed_key_len), fixed_vlen(c.fixed_val_len) {}
 
+  DeviceBuffer d_run_off, d_run_base, d_run_part, d_flags;
+  bool arrays_ready = false;   // the per-record metadata arrays (d_koff ...) are filled (never in run-table mode unless asked)
+  std::vector<uint64_t> h_counts, h_rec_base;
+
   void open(const tezgpu_segment *in, uint32_t nseg) {
     cudaStream_t st = pipe.stream;
     TG_CUDA(cudaSetDevice(pipe.conf.device));
     parsed_fixed = false;
+    arrays_ready = false;
     // ---- segments already on this device are used in place (no copy; kernels handle any byte alignment);
     //      host segments are staged contiguously with 16-byte aligned starts
     segs.resize(nseg);
@@ -412,15 +414,17 @@ class Merger {
         hi_addr = std::max(hi_addr, (uintptr_t)in[s].data + in[s].len);
       }
     lo_addr &= ~(uintptr_t)15;
+    bool any_header = false;
     for (uint32_t s = 0; s < nseg; s++) {
       TG_CHECK(in[s].data || in[s].len == 0, TEZGPU_E_INVALID, "null segment");
       const bool hdr = in[s].flags & TEZGPU_SEG_HAS_HEADER;
+      any_header |= hdr;
       TG_CHECK(in[s].len >= (hdr ? 10u : 6u), TEZGPU_E_FORMAT, "IFile segment shorter than an empty segment");
       segs[s].off = all_device ? (uint64_t)((uintptr_t)in[s].data - lo_addr) : off;
       segs[s].len = in[s].len;
       segs[s].body0 = hdr ? 4 : 0;
       segs[s].body_end = in[s].len - 4;
-      segs[s].has_header = hdr ? 1 : 0;
+      segs[s].has_header = (hdr ? 1u : 0u) | ((hdr && (in[s].flags & TEZGPU_SEG_VERIFIED)) ? 2u : 0u);
       segs[s].partition = in[s].partition;
       TG_CHECK((int)in[s].partition < pipe.conf.num_partitions, TEZGPU_E_INVALID, "segment partition out of range");
       off = align_up(off + in[s].len, 16);
@@ -443,113 +447,146 @@ class Merger {
     }
     d_segs.ensure((size_t)(nseg ? nseg : 1) * sizeof(SegDesc));
     if (nseg) TG_CUDA(cudaMemcpyAsync(d_segs.p, segs.data(), (size_t)nseg * sizeof(SegDesc), cudaMemcpyHostToDevice, st));
-    TG_CUDA(cudaMemsetAsync(pipe.small.p, 0, 16384, st));
-    if (nseg) {
-      k_check_headers<<<(uint32_t)div_up(nseg, 128), 128, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, pipe.d_error(),
-                                                                 pipe.d_error() + 1);
-      launches++;
-      int flags2[2] = {0, 0};
-      TG_CUDA(cudaMemcpyAsync(flags2, pipe.d_error(), 8, cudaMemcpyDeviceToHost, st));
-      TG_CUDA(cudaStreamSynchronize(st));  // also: the caller's host buffers may go away after open()
-      TG_CHECK(flags2[0] == 0, TEZGPU_E_FORMAT, "Not a valid ifile header (segment " + std::to_string(flags2[0] - 1) + ")");
-      TG_CHECK(flags2[1] == 0, TEZGPU_E_UNSUPPORTED, "compressed IFile segments are not supported on the device path");
-    }
-
+    // verdict words of the header / checksum checks: [0] bad magic, [1] compressed, [2] checksum mismatch (segment + 1).
+    // They live outside the sorter's scratch so the whole fixed-framing path needs no host round trip before the sort.
+    d_flags.ensure(64);
+    TG_CUDA(cudaMemsetAsync(d_flags.p, 0, 64, st));
+    int *d_vflags = d_flags.as<int>();
     const CrcTables *d_crc = DeviceConstants::get(pipe.conf.device).d_crc;
-    int *d_bad = pipe.d_error();
-    TG_CUDA(cudaMemsetAsync(pipe.small.p, 0, 16384, st));
     if (nseg) {
-      // ---- checksums
+      if (any_header) {
+        k_check_headers<<<(uint32_t)div_up(nseg, 128), 128, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, d_vflags, d_vflags + 1);
+        launches++;
+      }
+      // ---- checksums of the segments nobody verified yet
       std::vector<uint32_t> piece_start(nseg + 1);
       uint32_t np = 0;
       for (uint32_t s = 0; s < nseg; s++) {
         piece_start[s] = np;
-        np += (uint32_t)div_up(segs[s].body_end - segs[s].body0, CRC_PIECE);
+        if (segs[s].has_header == 1u) np += (uint32_t)div_up(segs[s].body_end - segs[s].body0, CRC_PIECE);
       }
       piece_start[nseg] = np;
-      d_piece_start.ensure((size_t)(nseg + 1) * 4);
-      TG_CUDA(cudaMemcpyAsync(d_piece_start.p, piece_start.data(), (size_t)(nseg + 1) * 4, cudaMemcpyHostToDevice, st));
-      d_piece_crc.ensure((size_t)(np ? np : 1) * sizeof(TileCrc));
-      d_seg_crc.ensure((size_t)nseg * 4);
-      TG_CUDA(cudaMemsetAsync(d_seg_crc.p, 0, (size_t)nseg * 4, st));
       if (np) {
+        d_piece_start.ensure((size_t)(nseg + 1) * 4);
+        TG_CUDA(cudaMemcpyAsync(d_piece_start.p, piece_start.data(), (size_t)(nseg + 1) * 4, cudaMemcpyHostToDevice, st));
+        TG_CUDA(cudaStreamSynchronize(st));  // piece_start is a stack-lifetime vector
+        d_piece_crc.ensure((size_t)np * sizeof(TileCrc));
+        d_seg_crc.ensure((size_t)nseg * 4);
+        TG_CUDA(cudaMemsetAsync(d_seg_crc.p, 0, (size_t)nseg * 4, st));
         k_crc_pieces<<<np, CRCV_THREADS, 0, st>>>(data, d_segs.as<SegDesc>(), d_piece_start.as<uint32_t>(), nseg, d_crc,
                                                   d_piece_crc.as<TileCrc>());
         k_crc_combine<<<(uint32_t)div_up(np, 256), 256, 0, st>>>(d_piece_crc.as<TileCrc>(), np, d_crc, d_seg_crc.as<uint32_t>());
-        launches += 2;
+        k_crc_check<<<(uint32_t)div_up(nseg, 128), 128, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, d_seg_crc.as<uint32_t>(), d_crc, d_vflags + 2);
+        launches += 3;
+        TG_CUDA(cudaGetLastError());
       }
-      k_crc_check<<<(uint32_t)div_up(nseg, 128), 128, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, d_seg_crc.as<uint32_t>(), d_crc, d_bad);
-      launches++;
-      TG_CUDA(cudaGetLastError());
-      int bad = 0;
-      TG_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
-      TG_CUDA(cudaStreamSynchronize(st));
-      TG_CHECK(bad == 0, TEZGPU_E_FORMAT, "IFile checksum mismatch in segment " + std::to_string(bad - 1));
     }
+    auto check_verdicts = [&]() {
+      int f[3] = {0, 0, 0};
+      TG_CUDA(cudaMemcpyAsync(f, d_vflags, 12, cudaMemcpyDeviceToHost, st));
+      TG_CUDA(cudaStreamSynchronize(st));
+      TG_CHECK(f[0] == 0, TEZGPU_E_FORMAT, "Not a valid ifile header (segment " + std::to_string(f[0] - 1) + ")");
+      TG_CHECK(f[1] == 0, TEZGPU_E_UNSUPPORTED, "compressed IFile segments are not supported on the device path");
+      TG_CHECK(f[2] == 0, TEZGPU_E_FORMAT, "IFile checksum mismatch in segment " + std::to_string(f[2] - 1));
+    };
 
-    // ---- parse: record counts per segment, then metadata
-    d_counts.ensure((size_t)(nseg + 1) * 16);
-    d_rec_base.ensure((size_t)(nseg + 2) * 8);
-    std::vector<uint64_t> counts(2 * (size_t)nseg + 2, 0), rec_base(nseg + 1, 0);
+    // ---- records per segment
+    h_counts.assign(2 * (size_t)nseg + 2, 0);
+    h_rec_base.assign(nseg + 1, 0);
     bool fixed_ok = false;
+    const uint32_t rs = vint_size_u32(fixed_klen) + vint_size_u32(fixed_vlen) + fixed_klen + fixed_vlen;
     if (nseg && fixed_klen + fixed_vlen > 0) {
       // candidate: every body is exactly k records of the fixed framing + EOF markers
-      const uint32_t rs = vint_size_u32(fixed_klen) + vint_size_u32(fixed_vlen) + fixed_klen + fixed_vlen;
       fixed_ok = true;
       for (uint32_t s = 0; s < nseg && fixed_ok; s++) {
         uint64_t body = segs[s].body_end - segs[s].body0;
         fixed_ok = body >= 2 && (body - 2) % rs == 0;
-        counts[s] = fixed_ok ? (body - 2) / rs : 0;
-        counts[nseg + s] = counts[s] * (fixed_klen + fixed_vlen);
+        h_counts[s] = fixed_ok ? (body - 2) / rs : 0;
+        h_counts[nseg + s] = h_counts[s] * (fixed_klen + fixed_vlen);
       }
     }
-    ParseArrays pa{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (nseg && !fixed_ok) {
-      k_parse_segments<false><<<(uint32_t)div_up(nseg, PARSE_WARPS), PARSE_WARPS * 32, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, d_counts.as<uint64_t>(),
-                                                                       d_counts.as<uint64_t>() + nseg, nullptr, pa, d_bad);
-      launches++;
-      TG_CUDA(cudaGetLastError());
-      int bad = 0;
-      TG_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, (size_t)nseg * 16, cudaMemcpyDeviceToHost, st));
-      TG_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
-      TG_CUDA(cudaStreamSynchronize(st));
-      TG_CHECK(bad == 0, TEZGPU_E_FORMAT, "malformed IFile segment " + std::to_string(bad - 1));
-    }
-    n = 0;
-    kv_bytes = 0;
-    for (uint32_t s = 0; s < nseg; s++) { rec_base[s] = n; n += counts[s]; kv_bytes += counts[nseg + s]; }
-    rec_base[nseg] = n;
-    TG_CHECK(n <= RADIX_MAX_N, TEZGPU_E_INVALID, "more than 2^30-1 records in one merge");
-    TG_CUDA(cudaMemcpyAsync(d_rec_base.p, rec_base.data(), (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, st));
-    d_koff.ensure((size_t)(n ? n : 1) * 8); d_voff.ensure((size_t)(n ? n : 1) * 8);
-    d_klen.ensure((size_t)(n ? n : 1) * 4); d_vlen.ensure((size_t)(n ? n : 1) * 4); d_tag.ensure((size_t)(n ? n : 1) * 4); d_part.ensure((size_t)(n ? n : 1) * 4);
-    pa = ParseArrays{d_koff.as<uint64_t>(), d_voff.as<uint64_t>(), d_klen.as<uint32_t>(), d_vlen.as<uint32_t>(), d_tag.as<uint32_t>(), d_part.as<int32_t>()};
-    if (n && fixed_ok) {
-      const uint32_t hl = vint_size_u32(fixed_klen) + vint_size_u32(fixed_vlen);
+    if (fixed_ok) {
+      // ---- run-table mode: offsets are arithmetic, the stage kernel checks the framing bytes it passes over anyway.
+      //      No per-record arrays, no host round trip before the sort's own.
+      n = 0;
+      kv_bytes = 0;
+      for (uint32_t s = 0; s < nseg; s++) { h_rec_base[s] = n; n += h_counts[s]; kv_bytes += h_counts[nseg + s]; }
+      h_rec_base[nseg] = n;
+      TG_CHECK(n <= RADIX_MAX_N, TEZGPU_E_INVALID, "more than 2^30-1 records in one merge");
+      std::vector<uint64_t> roff(nseg);
+      std::vector<uint32_t> rbase(nseg + 1), rpart(nseg);
+      for (uint32_t s = 0; s < nseg; s++) { roff[s] = segs[s].off + segs[s].body0; rbase[s] = (uint32_t)h_rec_base[s]; rpart[s] = segs[s].partition; }
+      rbase[nseg] = (uint32_t)n;
+      d_run_off.ensure((size_t)nseg * 8); d_run_base.ensure((size_t)(nseg + 1) * 4); d_run_part.ensure((size_t)nseg * 4);
+      TG_CUDA(cudaMemcpyAsync(d_run_off.p, roff.data(), (size_t)nseg * 8, cudaMemcpyHostToDevice, st));
+      TG_CUDA(cudaMemcpyAsync(d_run_base.p, rbase.data(), (size_t)(nseg + 1) * 4, cudaMemcpyHostToDevice, st));
+      TG_CUDA(cudaMemcpyAsync(d_run_part.p, rpart.data(), (size_t)nseg * 4, cudaMemcpyHostToDevice, st));
+      TG_CUDA(cudaStreamSynchronize(st));  // stack-lifetime staging vectors (and: the caller's host segments may go away)
+      Records r;
+      memset(&r, 0, sizeof(r));
+      r.kv = data;
+      r.kv_bytes = data_slack ? align_up(seg_bytes, 16) + data_slack : seg_bytes;
+      r.n = (uint32_t)n;
+      r.fixed = 1;
+      r.klen = fixed_klen;
+      r.vlen = fixed_vlen;
+      r.use_runs = 1;
+      r.runs.seg_off = d_run_off.as<uint64_t>();
+      r.runs.rec_base = d_run_base.as<uint32_t>();
+      r.runs.seg_part = d_run_part.as<uint32_t>();
+      r.runs.nseg = nseg;
+      r.runs.rec_size = rs;
+      r.runs.hdr_len = vint_size_u32(fixed_klen) + vint_size_u32(fixed_vlen);
       uint64_t hb = 0;
       int b = 0;
       for (int i = 0; i < vint_size_u32(fixed_klen); i++) hb |= (uint64_t)vint_byte_u32(fixed_klen, i) << (8 * b++);
       for (int i = 0; i < vint_size_u32(fixed_vlen); i++) hb |= (uint64_t)vint_byte_u32(fixed_vlen, i) << (8 * b++);
-      k_parse_fixed_check<<<(uint32_t)std::min<uint64_t>(div_up(n, 256), 148 * 16), 256, 0, st>>>(
-          data, d_segs.as<SegDesc>(), nseg, d_rec_base.as<uint64_t>(), fixed_klen, fixed_vlen, hl, hb, pa, pipe.d_error() + 1);
-      launches++;
-      int mism = 0;
-      TG_CUDA(cudaMemcpyAsync(&mism, pipe.d_error() + 1, 4, cudaMemcpyDeviceToHost, st));
-      TG_CUDA(cudaStreamSynchronize(st));
-      parsed_fixed = !mism;
-      if (mism) {
-        // not the fixed framing after all (e.g. run-length encoded input): take the general walk
-        open_general_reparse(nseg, counts, rec_base);
-        pa = ParseArrays{d_koff.as<uint64_t>(), d_voff.as<uint64_t>(), d_klen.as<uint32_t>(), d_vlen.as<uint32_t>(), d_tag.as<uint32_t>(), d_part.as<int32_t>()};
+      r.runs.hdr_bytes = hb;
+      bool mismatch = false;
+      pipe.merge_inputs_plain = true;
+      try {
+        pipe.sort_phase(r);
+      } catch (const FramingMismatch &) {
+        mismatch = true;  // not the fixed framing after all (e.g. run-length encoded input): take the general walk
       }
-    } else if (n) {
-      k_parse_segments<true><<<(uint32_t)div_up(nseg, PARSE_WARPS), PARSE_WARPS * 32, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, nullptr, nullptr,
-                                                                      d_rec_base.as<uint64_t>(), pa, d_bad);
-      launches++;
+      check_verdicts();
+      if (!mismatch) {
+        parsed_fixed = true;
+        launches += pipe.state.launches;
+        cursor = 0;
+        have_kvoff = false;
+        return;
+      }
+    } else {
+      check_verdicts();  // also: the caller's host buffers may go away after open()
     }
+
+    // ---- general path: walk the segments (IFile.Reader semantics), materialise the per-record metadata
+    int *d_bad = pipe.d_error();
+    TG_CUDA(cudaMemsetAsync(pipe.small.p, 0, 16384, st));
+    d_counts.ensure((size_t)(nseg + 1) * 16);
+    d_rec_base.ensure((size_t)(nseg + 2) * 8);
+    n = 0;
+    kv_bytes = 0;
+    if (nseg) open_general_reparse(nseg, h_counts, h_rec_base);
+    else {
+      d_koff.ensure(8); d_voff.ensure(8); d_klen.ensure(4); d_vlen.ensure(4); d_tag.ensure(4); d_part.ensure(4);
+    }
+    (void)d_bad;
     TG_CUDA(cudaGetLastError());
+    arrays_ready = true;
 
     // ---- merge = stable sort of the union of the runs by the RawComparator
+    Records r = array_records();
+    pipe.merge_inputs_plain = false;
+    pipe.sort_phase(r);
+    launches += pipe.state.launches;
+    cursor = 0;
+    have_kvoff = false;
+  }
+
+  // Records over the materialised per-record arrays
+  Records array_records() {
     Records r;
     memset(&r, 0, sizeof(r));
     r.kv = data;
@@ -562,16 +599,37 @@ class Merger {
     r.partition = pipe.conf.num_partitions > 1 ? d_part.as<int32_t>() : nullptr;
     r.n = (uint32_t)n;
     r.fixed = 0;
-    if (parsed_fixed && n) {  // every segment had the fixed framing: constant sizes, explicit offsets
-      r.fixed = 1;
-      r.klen = fixed_klen;
-      r.vlen = fixed_vlen;
+    return r;
+  }
+
+  // run-table mode keeps no per-record arrays; the record iterator and the general (run-length encoding) emit need
+  // them: fill them now (same record numbering, so the sorted order stays valid) and switch the sorter's view over
+  void ensure_arrays() {
+    if (arrays_ready) return;
+    cudaStream_t st = pipe.stream;
+    const uint32_t nseg = (uint32_t)segs.size();
+    d_rec_base.ensure((size_t)(nseg + 2) * 8);
+    TG_CUDA(cudaMemcpyAsync(d_rec_base.p, h_rec_base.data(), (size_t)(nseg + 1) * 8, cudaMemcpyHostToDevice, st));
+    d_koff.ensure((size_t)(n ? n : 1) * 8); d_voff.ensure((size_t)(n ? n : 1) * 8);
+    d_klen.ensure((size_t)(n ? n : 1) * 4); d_vlen.ensure((size_t)(n ? n : 1) * 4); d_tag.ensure((size_t)(n ? n : 1) * 4); d_part.ensure((size_t)(n ? n : 1) * 4);
+    ParseArrays pa{d_koff.as<uint64_t>(), d_voff.as<uint64_t>(), d_klen.as<uint32_t>(), d_vlen.as<uint32_t>(), d_tag.as<uint32_t>(), d_part.as<int32_t>()};
+    if (n) {
+      const uint32_t hl = vint_size_u32(fixed_klen) + vint_size_u32(fixed_vlen);
+      k_fill_fixed_arrays<<<(uint32_t)std::min<uint64_t>(div_up(n, 256), 148 * 16), 256, 0, st>>>(
+          d_segs.as<SegDesc>(), nseg, d_rec_base.as<uint64_t>(), fixed_klen, fixed_vlen, hl, pa);
+      launches++;
+      TG_CUDA(cudaGetLastError());
     }
-    pipe.merge_inputs_plain = parsed_fixed;
-    pipe.sort_phase(r);
-    launches += pipe.state.launches;
-    cursor = 0;
-    have_kvoff = false;
+    Records r = array_records();
+    r.fixed = 1;
+    r.klen = fixed_klen;
+    r.vlen = fixed_vlen;
+    r.cmp = pipe.state.rec.cmp;
+    r.hash_partition = pipe.state.rec.hash_partition;
+    r.num_partitions = pipe.state.rec.num_partitions;
+    r.pbits = pipe.state.rec.pbits;
+    pipe.state.rec = r;
+    arrays_ready = true;
   }
 
   void open_general_reparse(uint32_t nseg, std::vector<uint64_t> &counts, std::vector<uint64_t> &rec_base) {
@@ -627,6 +685,7 @@ class Merger {
 
   void ensure_kvoff() {
     if (have_kvoff) return;
+    ensure_arrays();
     cudaStream_t st = pipe.stream;
     const uint32_t nn = (uint32_t)n;
     d_sizes.ensure((size_t)(nn ? nn : 1) * 4);

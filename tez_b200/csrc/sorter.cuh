@@ -39,6 +39,9 @@ struct DeviceConstants {
   }
 };
 
+// thrown by sort_phase in run-table mode (Records::use_runs): the merger then re-parses the segments with the walker
+struct FramingMismatch {};
+
 class SortPipeline {
  public:
   tezgpu_conf conf;
@@ -158,7 +161,7 @@ class SortPipeline {
       // the pipelined kernel for records at arbitrary offsets (emit_pipe_u.cuh) holds a tile's words in five gather rounds
       const uint32_t stride = rec.klen + rec.vlen;
       const bool fast = stride >= 16 && stride % 16 == 0;
-      const bool aligned = !rec.key_off && (((uintptr_t)rec.kv & 15u) == 0);
+      const bool aligned = !rec.key_off && !rec.use_runs && (((uintptr_t)rec.kv & 15u) == 0);
       if (fast && !aligned && emit4u_max_recs(stride / 16) >= 32) {
         e.recs_per_tile = std::min<uint32_t>(e.recs_per_tile, emit4u_max_recs(stride / 16));
         fill = true;
@@ -198,7 +201,7 @@ class SortPipeline {
     rec.hash_partition = conf.partitioner == TEZGPU_PART_HASH;
     rec.num_partitions = P;
     rec.pbits = pbits;
-    TG_CHECK(rec.hash_partition || rec.partition || n == 0 || P == 1, TEZGPU_E_INVALID, "partition ids required (partitioner=GIVEN)");
+    TG_CHECK(rec.hash_partition || rec.partition || rec.use_runs || n == 0 || P == 1, TEZGPU_E_INVALID, "partition ids required (partitioner=GIVEN)");
     int launches = 0;
     state.have_bounds = state.spec_layout = false;
     timer.reset();
@@ -227,7 +230,7 @@ class SortPipeline {
     if (n) {
       // ---------------- stage
       TG_CUDA(cudaMemsetAsync(same.p, 0, n, stream));
-      const bool fast16 = rec.fixed && !rec.key_off && rec.klen == 16 && ((rec.klen + rec.vlen) % 16 == 0) && rec.cmp == CMP_BYTES &&
+      const bool fast16 = rec.fixed && !rec.key_off && !rec.use_runs && rec.klen == 16 && ((rec.klen + rec.vlen) % 16 == 0) && rec.cmp == CMP_BYTES &&
                           (((uintptr_t)rec.kv & 15u) == 0);
       int sgrid = (int)std::min<uint64_t>(div_up(n, 256), 148 * 16);
       if (fast16) k_stage<true><<<sgrid, 256, 0, stream>>>(rec, K, d_hist(), d_error());
@@ -280,7 +283,8 @@ class SortPipeline {
         TG_CUDA(cudaMemcpyAsync(h_small.as<uint8_t>() + 4096, d_index.p, (size_t)P * 24, cudaMemcpyDeviceToHost, stream));
       TG_CUDA(cudaStreamSynchronize(stream));
       // words: [0] error, [1] large groups, [2..3] duplicates, [4..7] layout totals, [8] tied records
-      TG_CHECK(hw[0] == 0, TEZGPU_E_INVALID, "Illegal partition (outside [0, numPartitions))");
+      TG_CHECK(!(hw[0] & 1u), TEZGPU_E_INVALID, "Illegal partition (outside [0, numPartitions))");
+      if (hw[0] & 2u) throw FramingMismatch();  // run-table mode: some record position lacks the fixed framing bytes
       uint32_t m = hw[8];
       tie_records = m;
       memcpy(&dup_count, hw + 2, 8);
@@ -430,7 +434,7 @@ class SortPipeline {
     // 128-bit load per piece, records at explicit / unaligned offsets two loads + a funnel shift
     const uint32_t stride = rec.klen + rec.vlen;
     const bool fast_emit = fixed_emit && stride >= 16 && (stride % 16 == 0) && !getenv("TEZGPU_NO_FAST_EMIT");
-    const bool fast_aligned = fast_emit && !rec.key_off && (((uintptr_t)rec.kv & 15u) == 0);
+    const bool fast_aligned = fast_emit && !rec.key_off && !rec.use_runs && (((uintptr_t)rec.kv & 15u) == 0);
     FastEmitParams fp;
     if (tiles && fast_emit) {
       tile_desc.ensure((size_t)tiles * sizeof(TileDesc));

@@ -11,6 +11,34 @@
 
 namespace tezgpu {
 
+// Fixed-framing IFile runs read in place (reduce side of the device shuffle): record i of the merge lives in segment
+// s = last segment with rec_base[s] <= i, at body offset (i - rec_base[s]) * rec_size -- pure arithmetic, so no
+// per-record metadata arrays exist at all (they were 32 B per record of extra HBM traffic each way).
+struct RunTable {
+  const uint64_t *seg_off;    // [nseg] offset in kv of the first record (its framing bytes) of every segment
+  const uint32_t *rec_base;   // [nseg + 1] first merge record index of every segment
+  const uint32_t *seg_part;   // [nseg] output partition of every segment
+  uint32_t nseg;
+  uint32_t rec_size;          // framing + key + value bytes
+  uint32_t hdr_len;           // framing bytes: vint(klen) vint(vlen)
+  uint64_t hdr_bytes;         // the framing bytes, little-endian packed (checked by k_stage)
+};
+
+// last segment s with rec_base[s] <= i (rec_base is small and hot in L1)
+__device__ __forceinline__ uint32_t run_of(const RunTable &t, uint32_t i) {
+  uint32_t lo = 0, hi = t.nseg;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(t.rec_base + mid) <= i) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+// byte offset in kv of record i's framing bytes
+__device__ __forceinline__ uint64_t run_record_off(const RunTable &t, uint32_t i, uint32_t &seg) {
+  seg = run_of(t, i);
+  return __ldg(t.seg_off + seg) + (uint64_t)(i - __ldg(t.rec_base + seg)) * t.rec_size;
+}
+
 // Collected records as they sit in HBM (the analogue of PipelinedSorter's kvbuffer + kvmeta, :957-959)
 struct Records {
   const uint8_t *kv;        // serialized bytes, key immediately followed by value
@@ -28,13 +56,21 @@ struct Records {
   int hash_partition;
   int num_partitions;
   int pbits;  // bits of the sort word that hold the partition
+  int use_runs;   // fixed mode: records are addressed through `runs` instead of index * stride / key_off
+  RunTable runs;
 };
 
 __device__ __forceinline__ void record_lookup(const Records &r, uint32_t i, uint64_t &koff, uint32_t &klen,
                                               uint32_t &vlen) {
   if (r.fixed) {
-    // fixed framing; key_off present = records live at explicit offsets (parsed fixed-width IFile segments)
-    koff = r.key_off ? r.key_off[i] : (uint64_t)i * (r.klen + r.vlen);
+    // fixed framing; key_off present = records live at explicit offsets (parsed fixed-width IFile segments);
+    // use_runs = offsets are arithmetic over the segment table
+    if (r.use_runs) {
+      uint32_t seg;
+      koff = run_record_off(r.runs, i, seg) + r.runs.hdr_len;
+    } else {
+      koff = r.key_off ? r.key_off[i] : (uint64_t)i * (r.klen + r.vlen);
+    }
     klen = r.klen;
     vlen = r.vlen;
   } else {
@@ -42,6 +78,11 @@ __device__ __forceinline__ void record_lookup(const Records &r, uint32_t i, uint
     klen = r.key_len[i];
     vlen = r.val_len[i];
   }
+}
+
+// merge only: (segment id << 1) | record was run-length encoded in its input segment
+__device__ __forceinline__ uint32_t record_tag(const Records &r, uint32_t i) {
+  return (r.fixed && r.use_runs) ? run_of(r.runs, i) << 1 : r.tag[i];
 }
 
 // ------------------------------------------------------------------------------------------------ stage
@@ -74,7 +115,22 @@ __global__ void __launch_bounds__(256) k_stage(Records r, uint32_t *__restrict__
     } else {
       uint64_t koff;
       uint32_t klen, vlen;
-      record_lookup(r, i, koff, klen, vlen);
+      int32_t run_part = 0;
+      if (r.fixed && r.use_runs) {
+        uint32_t seg;
+        const uint64_t roff = run_record_off(r.runs, i, seg);
+        koff = roff + r.runs.hdr_len;
+        klen = r.klen;
+        vlen = r.vlen;
+        run_part = (int32_t)__ldg(r.runs.seg_part + seg);
+        // the sequential IFile.Reader walk visits exactly these positions iff every one of them carries the fixed
+        // framing bytes (same sector as the key: free); a mismatch sends the merge to the general parser
+        bool ok = true;
+        for (uint32_t b = 0; b < r.runs.hdr_len; b++) ok &= r.kv[roff + b] == (uint8_t)(r.runs.hdr_bytes >> (8 * b));
+        if (!ok) atomicOr(error_flag, 2);
+      } else {
+        record_lookup(r, i, koff, klen, vlen);
+      }
       const uint8_t *key = r.kv + koff;
       uint32_t skip = key_content_skip(r.cmp, key, klen);
       const uint8_t *content = key + skip;
@@ -83,10 +139,10 @@ __global__ void __launch_bounds__(256) k_stage(Records r, uint32_t *__restrict__
 #pragma unroll
       for (uint32_t b = 0; b < 4; b++) prefix = (prefix << 8) | (b < clen ? norm_byte(r.cmp, content, b) : 0u);
       p = r.hash_partition ? (int32_t)((uint32_t)(key_hash_dev(r.cmp, key, klen) & 0x7fffffff) % (uint32_t)r.num_partitions)
-                           : (r.partition ? r.partition[i] : 0);
+                           : ((r.fixed && r.use_runs) ? run_part : (r.partition ? r.partition[i] : 0));
     }
     if (p < 0 || p >= r.num_partitions) {
-      *error_flag = 1;  // "Illegal partition" (PipelinedSorter.java:410-413)
+      atomicOr(error_flag, 1);  // "Illegal partition" (PipelinedSorter.java:410-413)
       p = 0;
     }
     uint32_t K = r.pbits ? (((uint32_t)p << (32 - r.pbits)) | (prefix >> r.pbits)) : prefix;
@@ -463,9 +519,9 @@ __device__ __forceinline__ bool emit_is_repeat(const EmitParams &e, uint32_t r, 
   if (!e.merge_mode) return writer;
   // read as SAME_KEY from its own segment; with checkForSameKeys also "the top segment changed and its key equals the
   // previous key" (compareKeyWithNextTopKey, :640-652)
-  const uint32_t tag = rec.tag[i];
+  const uint32_t tag = record_tag(rec, i);
   if (writer || (tag & 1u)) return true;
-  return e.check_same && ((tag >> 1) != (rec.tag[e.order[r - 1]] >> 1));
+  return e.check_same && ((tag >> 1) != (record_tag(rec, e.order[r - 1]) >> 1));
 }
 
 // var mode: emitted size of the record at sorted position r (IFile.Writer.writeKVPair / writeValue / markers,

@@ -5,6 +5,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <mutex>
 #include <string>
 
 #include "../../include/tezgpu.h"
@@ -407,6 +408,80 @@ int32_t tezgpu_fetch_ranges(int32_t device, const tezgpu_copy_range *ranges, uin
   if (e1) cudaEventDestroy(e1);
   if (d_fr) cudaFree(d_fr);
   TG_CUDA(err);
+  TG_API_END
+}
+
+// per-device scratch of tezgpu_fetch_ranges_verified (grow-only; one fetch at a time per device)
+struct FetchVerifyScratch {
+  DeviceBuffer segs, piece_start, piece_crc, seg_crc, flag;
+  std::mutex mu;
+};
+static FetchVerifyScratch &fetch_scratch(int device) {
+  static FetchVerifyScratch inst[64];
+  return inst[device & 63];
+}
+
+int32_t tezgpu_fetch_segments_verified(int32_t device, const tezgpu_fetch_segment *segs, uint32_t n, void *stream,
+                                       float *ms_kernel) {
+  TG_API_BEGIN
+  TG_CHECK(segs || n == 0, TEZGPU_E_INVALID, "null argument");
+  if (ms_kernel) *ms_kernel = 0;
+  if (n == 0) return TEZGPU_OK;
+  TG_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<FetchSeg> fs(n);
+  std::vector<uint32_t> piece_start(n + 1);
+  uint32_t np = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const bool hdr = segs[i].flags & TEZGPU_SEG_HAS_HEADER;
+    TG_CHECK(segs[i].src && segs[i].dst, TEZGPU_E_INVALID, "null segment");
+    TG_CHECK(segs[i].len >= (hdr ? 10u : 6u), TEZGPU_E_FORMAT, "IFile segment shorter than an empty segment");
+    TG_CHECK((((uintptr_t)segs[i].src ^ (uintptr_t)segs[i].dst) & 15u) == 0, TEZGPU_E_INVALID,
+             "source and destination of a verified fetch must agree modulo 16");
+    fs[i].src = (const uint8_t *)segs[i].src;
+    fs[i].dst = (uint8_t *)segs[i].dst;
+    fs[i].len = segs[i].len;
+    fs[i].has_header = hdr ? 1 : 0;
+    fs[i].pad = 0;
+    piece_start[i] = np;
+    np += (uint32_t)div_up(segs[i].len - 4 - (hdr ? 4 : 0), FV_PIECE);
+  }
+  piece_start[n] = np;
+  FetchVerifyScratch &sc = fetch_scratch(device);
+  std::lock_guard<std::mutex> lock(sc.mu);
+  sc.segs.ensure((size_t)n * sizeof(FetchSeg));
+  sc.piece_start.ensure((size_t)(n + 1) * 4);
+  sc.piece_crc.ensure((size_t)np * sizeof(TileCrc));
+  sc.seg_crc.ensure((size_t)n * 4);
+  sc.flag.ensure(16);
+  const CrcTables *d_crc = DeviceConstants::get(device).d_crc;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  TG_CUDA(cudaMemcpyAsync(sc.segs.p, fs.data(), (size_t)n * sizeof(FetchSeg), cudaMemcpyHostToDevice, st));
+  TG_CUDA(cudaMemcpyAsync(sc.piece_start.p, piece_start.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+  TG_CUDA(cudaMemsetAsync(sc.seg_crc.p, 0, (size_t)n * 4, st));
+  TG_CUDA(cudaMemsetAsync(sc.flag.p, 0, 16, st));
+  if (ms_kernel) {
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+  }
+  int sms = 148, per_sm = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fetch_verify, FV_THREADS, 0);
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(np, (uint64_t)sms * (per_sm > 0 ? per_sm : 1));
+  k_fetch_verify<<<grid, FV_THREADS, 0, st>>>(sc.segs.as<FetchSeg>(), sc.piece_start.as<uint32_t>(), n, np, d_crc, sc.piece_crc.as<TileCrc>());
+  if (ms_kernel) cudaEventRecord(e1, st);
+  k_crc_combine<<<(uint32_t)div_up(np, 256), 256, 0, st>>>(sc.piece_crc.as<TileCrc>(), np, d_crc, sc.seg_crc.as<uint32_t>());
+  k_fetch_crc_check<<<(uint32_t)div_up(n, 128), 128, 0, st>>>(sc.segs.as<FetchSeg>(), n, sc.seg_crc.as<uint32_t>(), d_crc, sc.flag.as<int>());
+  cudaError_t err = cudaGetLastError();
+  int bad = 0;
+  if (err == cudaSuccess) err = cudaMemcpyAsync(&bad, sc.flag.p, 4, cudaMemcpyDeviceToHost, st);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+  if (err == cudaSuccess && ms_kernel) cudaEventElapsedTime(ms_kernel, e0, e1);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  TG_CUDA(err);
+  TG_CHECK(bad == 0, TEZGPU_E_FORMAT, "IFile checksum mismatch in fetched segment " + std::to_string(bad - 1));
   TG_API_END
 }
 

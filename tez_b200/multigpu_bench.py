@@ -73,11 +73,12 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
         # the library works on its own stream: the received bytes must have landed before it reads them
         torch.cuda.current_stream().synchronize()
         parts = [p for _, _, p, _ in segs]
+        verified = px.last_verified if px else None
         if merger[0] is None:
             merger[0] = T.GpuMerger(seg_list, comparator=T.CMP_BYTES, device=local, device_ptrs=True,
-                                    fixed=(KEY_LEN, VAL_LEN), partitions=parts, num_partitions=p1 - p0)
+                                    fixed=(KEY_LEN, VAL_LEN), partitions=parts, num_partitions=p1 - p0, verified=verified)
         else:
-            merger[0].reopen(seg_list, parts)
+            merger[0].reopen(seg_list, parts, verified=verified)
         m = merger[0]
         mlen, mindex, mst = m.write_partitions_device(d_merged.data_ptr(), d_merged.numel())
         nrec, _ = m.counts()
@@ -120,11 +121,12 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
             e[1].record()
             seg_list = [(ptr, ln) for ptr, ln, _, _ in segs]
             parts = [p for _, _, p, _ in segs]
+            verified = px.last_verified
             if merger[0] is None:
                 merger[0] = T.GpuMerger(seg_list, comparator=T.CMP_BYTES, device=local, device_ptrs=True,
-                                        fixed=(KEY_LEN, VAL_LEN), partitions=parts, num_partitions=p1 - p0)
+                                        fixed=(KEY_LEN, VAL_LEN), partitions=parts, num_partitions=p1 - p0, verified=verified)
             else:
-                merger[0].reopen(seg_list, parts)
+                merger[0].reopen(seg_list, parts, verified=verified)
             m = merger[0]
             mlen, mindex, mst = m.write_partitions_device(d_merged.data_ptr(), d_merged.numel())
             nrec, _ = m.counts()

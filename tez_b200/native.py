@@ -116,18 +116,20 @@ class GpuSorter:
 
 class GpuMerger:
     def __init__(self, segments, comparator=CMP_BYTES, device=0, has_header=True, device_ptrs=False, fixed=None,
-                 partitions=None, num_partitions=1, send_empty=True):
-        """segments: list of bytes / uint8 arrays (host) or (ptr, len) tuples when device_ptrs."""
+                 partitions=None, num_partitions=1, send_empty=True, verified=None):
+        """segments: list of bytes / uint8 arrays (host) or (ptr, len) tuples when device_ptrs.
+        verified: optional per-segment booleans -- the transport already checked that segment's checksum
+        (TEZGPU_SEG_VERIFIED: fetch_segments_verified), the merge does not read it again to verify."""
         self.L = _lib.load()
         self.conf = make_conf(num_partitions, comparator=comparator, partitioner=PART_GIVEN, device=device, fixed=fixed,
                               send_empty=send_empty)
         self.P = num_partitions
         self._has_header, self._device_ptrs = has_header, device_ptrs
-        arr = self._segments(segments, partitions)
+        arr = self._segments(segments, partitions, verified)
         self.h = C.c_void_p()
         check(self.L.tezgpu_merge_open(C.byref(self.conf), arr, len(segments), C.byref(self.h)))
 
-    def _segments(self, segments, partitions):
+    def _segments(self, segments, partitions, verified=None):
         self._keep = []
         arr = (Segment * max(1, len(segments)))()
         flags = (SEG_HAS_HEADER if self._has_header else 0) | (SEG_DEVICE if self._device_ptrs else 0)
@@ -136,6 +138,8 @@ class GpuMerger:
             tab = np.zeros(len(segments), dtype=np.dtype([("data", "<u8"), ("len", "<u8"), ("flags", "<u4"), ("partition", "<u4")]))
             sp = np.asarray(segments, dtype=np.uint64).reshape(-1, 2)
             tab["data"], tab["len"], tab["flags"] = sp[:, 0], sp[:, 1], flags
+            if verified is not None:
+                tab["flags"] |= np.where(np.asarray(verified, dtype=bool), SEG_VERIFIED, 0).astype(np.uint32)
             if partitions is not None:
                 tab["partition"] = np.asarray(partitions, dtype=np.uint32)
             self._keep.append(tab)
@@ -148,13 +152,13 @@ class GpuMerger:
                 self._keep.append(a)
                 arr[i].data = a.ctypes.data if a.size else None
                 arr[i].len = a.size
-            arr[i].flags = flags
+            arr[i].flags = flags | (SEG_VERIFIED if (verified is not None and verified[i]) else 0)
             arr[i].partition = 0 if partitions is None else int(partitions[i])
         return arr
 
-    def reopen(self, segments, partitions=None):
+    def reopen(self, segments, partitions=None, verified=None):
         """New merge through the same handle (device allocations are kept)."""
-        arr = self._segments(segments, partitions)
+        arr = self._segments(segments, partitions, verified)
         check(self.L.tezgpu_merge_reopen(self.h, arr, len(segments)))
 
     def close(self):
@@ -261,6 +265,24 @@ class PeerMapping:
         if self.ptr:
             check(self.L.tezgpu_peer_close(self.device, self.ptr))
             self.ptr = None
+
+
+FETCH_SEG_DTYPE = np.dtype([("src", "<u8"), ("dst", "<u8"), ("len", "<u8"), ("flags", "<u4"), ("reserved", "<u4")])
+
+
+def fetch_segments_verified(segs, device=0, stream=None, has_header=True):
+    """segs: iterable of (src_ptr, dst_ptr, nbytes) -- one IFile segment each.  One launch copies them and verifies every
+    segment's CRC32 trailer on the bytes in flight (IFile.Reader.readToMemory); raises TezGpuError(TEZGPU_E_FORMAT) on a
+    mismatch.  Returns the copy kernel's time in ms."""
+    L = _lib.load()
+    tab = np.zeros(len(segs), dtype=FETCH_SEG_DTYPE)
+    if len(segs):
+        a = np.asarray(segs, dtype=np.uint64).reshape(-1, 3)
+        tab["src"], tab["dst"], tab["len"] = a[:, 0], a[:, 1], a[:, 2]
+        tab["flags"] = SEG_HAS_HEADER if has_header else 0
+    ms = C.c_float()
+    check(L.tezgpu_fetch_segments_verified(device, tab.ctypes.data, len(segs), stream, C.byref(ms)))
+    return ms.value
 
 
 def fetch_ranges(ranges, device=0, stream=None):

@@ -96,7 +96,8 @@ def pull_plan(all_idx, rank, num_partitions, peer_ptrs):
 
 def pull_segments(all_idx, rank, num_partitions, peer_ptrs, seg_src, recv_base):
     """Segment table after the pull: [(address, length, local_partition, source_rank)] ordered by (source_rank,
-    partition) -- the order TezMerger breaks ties in.  Own runs stay where the sorter wrote them."""
+    partition) -- the order TezMerger breaks ties in.  Own runs stay where the sorter wrote them.  (The merge sorts by
+    (partition, key) and breaks ties by position in this table, i.e. by source rank inside a partition.)"""
     world = all_idx.shape[0]
     p0, p1 = owner_ranges(num_partitions, world)[rank]
     starts = all_idx[:, p0:p1, 0]
@@ -126,6 +127,9 @@ class PeerExchange:
         self.slots, self._maps, self.peers = [], [], []
         self._recv = None
         self.last_fetch_ms = 0.0
+        self.last_verified = None
+        import os
+        self.verify = os.environ.get("TEZ_SHUFFLE_VERIFY_IN_FETCH", "1") != "0"
         # every phase ends in a consensus (all-reduce MIN of a success flag): either all ranks get the peer transport
         # or all of them raise, so a caller can fall back to exchange_partitions() without a collective mismatch
         err = None
@@ -181,8 +185,19 @@ class PeerExchange:
         if self._recv is None or self._recv.numel() < need + 64:
             self._recv = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, device=torch.device("cuda", self.device))
         base = self._recv.data_ptr()
-        self.last_fetch_ms = native.fetch_ranges([(src, base + off, ln) for _, src, off, ln in ranges], self.device, stream)
-        return pull_segments(all_idx, self.rank, num_partitions, peer_ptrs, seg_src, base)
+        segs = pull_segments(all_idx, self.rank, num_partitions, peer_ptrs, seg_src, base)
+        if self.verify:
+            # one kernel moves the remote segments AND verifies each one's CRC32 trailer on the bytes in flight, like
+            # IFile.Reader.readToMemory on a fetch to memory (SORT/IFile.java:764-809); own runs are verified by the merge
+            p0 = owner_ranges(num_partitions, self.world)[self.rank][0]
+            src_of = {g: (peer_ptrs[g] + a) - (base + off) for g, (off, a) in seg_src.items()}   # src - dst per producer
+            remote = [(ptr + src_of[g], ptr, ln) for ptr, ln, _, g in segs if g != self.rank]
+            self.last_fetch_ms = native.fetch_segments_verified(remote, self.device, stream)
+            self.last_verified = [g != self.rank for _, _, _, g in segs]
+        else:
+            self.last_fetch_ms = native.fetch_ranges([(src, base + off, ln) for _, src, off, ln in ranges], self.device, stream)
+            self.last_verified = None
+        return segs
 
     def close(self):
         for m in self._maps:
