@@ -240,6 +240,11 @@ int32_t tezgpu_fetch_segments_verified(int32_t device, const tezgpu_fetch_segmen
 /* diagnostics: host-side emulation of the device's tiled CRC algebra (same tables, no GPU needed) */
 uint32_t tezgpu_debug_crc_emulate(const uint8_t *body, uint64_t len, uint32_t piece_bytes, uint32_t lead);
 
+/* diagnostics: host-side run of the TMA emit kernel's chunk assembly (same template code, no GPU needed) */
+uint32_t tezgpu_debug_assemble_emulate(const uint8_t *stage, uint32_t nr, uint32_t stride, const uint8_t *hdr,
+                                       uint32_t hdr_len, uint32_t lead, int32_t first, int32_t last, uint8_t *image_out,
+                                       uint32_t image_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,3 +40,39 @@ def test_segment_table_fast_path_matches_ctypes_layout():
     assert fast_bytes == bytes(slow)
     few = m._segments(segs[:3], parts[:3])        # the ctypes path (<= 64 runs)
     assert bytes(few)[:3 * 24] == bytes(slow)[:3 * 24]
+
+
+def test_tma_emit_chunk_assembly_matches_the_byte_image():
+    """The TMA emit kernel (emit_tma.cuh) never builds the output image in shared memory: every aligned 16-byte chunk is
+    assembled straight from the staged records (framing bytes, record straddles, segment header, EOF markers).  The same
+    template code runs here on the host (tezgpu_debug_assemble_emulate) against the obvious concatenation, for record
+    strides / vint framings / tile sizes / alignments / first-last flags the kernel can meet."""
+    import numpy as np
+    L = _lib.load()
+    rng = random.Random(1)
+    cases = 0
+    for stride in (16, 32, 80, 96, 4112):
+        for hdr in (b"\x10\x40", b"\x10", b"\x8f\x80\x40", b"\x8f\x80\x8e\x10\x00", bytes(range(1, 11))):
+            for nr in (1, 2, 3, 17, 255, 256):
+                if nr * stride > 300000:
+                    continue
+                for lead in (0, 1, 2, 7, 12, 13, 15):
+                    for first in (0, 1):
+                        for last in (0, 1):
+                            stage = np.frombuffer(rng.randbytes(nr * stride), dtype=np.uint8).copy()
+                            img = bytearray(lead)
+                            if first:
+                                img += b"TIF\x00"
+                            for j in range(nr):
+                                img += hdr + stage[j * stride:(j + 1) * stride].tobytes()
+                            if last:
+                                img += b"\xff\xff"
+                            cap = (len(img) + 31) // 16 * 16
+                            out = np.zeros(cap, dtype=np.uint8)
+                            hb = np.frombuffer(hdr, dtype=np.uint8).copy()
+                            end = L.tezgpu_debug_assemble_emulate(stage.ctypes.data, nr, stride, hb.ctypes.data, len(hdr), lead,
+                                                                  first, last, out.ctypes.data, cap)
+                            assert end == len(img)
+                            assert out[lead:end].tobytes() == bytes(img[lead:]), (stride, hdr, nr, lead, first, last)
+                            cases += 1
+    assert cases > 3000

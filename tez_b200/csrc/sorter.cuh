@@ -12,6 +12,7 @@
 #define TEZGPU_EMIT_ROUND_FILL_DEFAULT 0
 #endif
 #include "emit_pipe_u.cuh"
+#include "emit_tma.cuh"
 #include "sorter_kernels.cuh"
 
 namespace tezgpu {
@@ -453,7 +454,20 @@ class SortPipeline {
     if (tiles) {
       if (fast_emit) {
         int per_sm = 0;
-        if (fast_aligned && emit4_fits(e.recs_per_tile, fp.cpr) && !getenv("TEZGPU_EMIT_V2")) {
+        static const bool use_tma = !(getenv("TEZGPU_EMIT_TMA") && atoi(getenv("TEZGPU_EMIT_TMA")) == 0);
+        if (fast_aligned && use_tma && emit_tma_fits(e.recs_per_tile, stride)) {
+          // gather by the bulk-copy engine into a shared-memory ring, chunks assembled straight from the staged
+          // records (emit_tma.cuh); TEZGPU_EMIT_TMA=0 selects the register-staged kernels below
+          const size_t smem = EmitTmaLayout::total(e.recs_per_tile, stride);
+          static size_t attr_smem = 0;
+          if (smem > attr_smem) {
+            TG_CUDA(cudaFuncSetAttribute(k_emit_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem = smem;
+          }
+          TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_tma, ET_THREADS, smem));
+          uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));
+          k_emit_tma<<<grid, ET_THREADS, smem, stream>>>(fp, (uint32_t)EmitTmaLayout::stage_bytes(e.recs_per_tile, stride));
+        } else if (fast_aligned && emit4_fits(e.recs_per_tile, fp.cpr) && !getenv("TEZGPU_EMIT_V2")) {
           // software-pipelined kernel (emit_pipe.cuh): a tile's pieces must fit the registers of one gather round.
           // Default: independent 256-thread CTAs, three per SM.  TEZGPU_EMIT_SUBS=3 selects the variant with one CTA
           // per SM whose three groups share lane-private checksum tables -- measured SLOWER (8.39 vs 5.44 ms): its
