@@ -260,6 +260,48 @@ def single_gpu(args):
                 "ms": {"stage": round(sum(stage_ms) / len(stage_ms), 4), "sort": round(sum(sort_ms) / len(sort_ms), 4),
                        "ties": round(sum(ties_ms) / len(ties_ms), 4), "emit_kernel": round(emit, 4)}}
 
+    # ---- the N>1 pipeline at G=1 (BASELINE config 4 shape on one GPU: sort into 1024 partitions, no exchange, batched
+    # device merge of the single run of every partition) so that the 1->N curve can also be read like for like: the
+    # N=1 headline above is config 2 (sort only, P=64), the N>1 lines are sort + exchange + merge (P=1024).
+    pipeline_g1 = None
+    if not args.no_g1_pipeline:
+        P4 = 1024
+        s4 = T.GpuSorter(P4, fixed=(KEY_LEN, VAL_LEN), device=0)
+        cap4 = n * OUT_REC + 10 * P4 + 4096
+        d_out4 = torch.empty(cap4, dtype=torch.uint8, device=dev)
+        d_merged = torch.empty(cap4 + (1 << 20), dtype=torch.uint8, device=dev)
+        mg = [None]
+
+        def step4():
+            out_len4, index4, st4 = s4.sort_device_fixed(d_kv.data_ptr(), n, d_out4.data_ptr(), cap4)
+            segs4 = [(d_out4.data_ptr() + int(index4[p, 0]), int(index4[p, 2])) for p in range(P4) if index4[p, 2]]
+            parts4 = [p for p in range(P4) if index4[p, 2]]
+            if mg[0] is None:
+                mg[0] = T.GpuMerger(segs4, comparator=T.CMP_BYTES, device=0, device_ptrs=True, fixed=(KEY_LEN, VAL_LEN),
+                                    partitions=parts4, num_partitions=P4)
+            else:
+                mg[0].reopen(segs4, parts4)
+            mlen4, mindex4, mst4 = mg[0].write_partitions_device(d_merged.data_ptr(), d_merged.numel())
+            return st4, mst4, mlen4, out_len4
+
+        for _ in range(2):
+            step4()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        k4 = max(3, min(args.steps, 5))
+        for _ in range(k4):
+            st4, mst4, mlen4, out_len4 = step4()
+        torch.cuda.synchronize()
+        ms4 = (time.perf_counter() - t0) / k4 * 1e3
+        assert mlen4 == out_len4       # one run per partition: the merge reproduces the sorter's file.out length
+        pipeline_g1 = {"workload": "config 4 shape at G=1: %d records, 1024 partitions, sort + batched merge (no exchange)" % n,
+                       "ms_per_step": round(ms4, 3), "value": round(n * REC / (ms4 * 1e-3) / 1e9, 1), "unit": "GB/s",
+                       "ms_sort": round(st4["ms_total"], 3), "ms_merge_emit": round(mst4["ms_emit"], 3),
+                       "timing": "host clock around fully synchronised library calls, %d steps" % k4}
+        mg[0].close()
+        s4.close()
+        del d_out4, d_merged
+
     # ---- e2e through the C ABI with host buffers (pinned), H2D + D2H inside the timed region.
     # Two task slots (as a node runs several map tasks per GPU): each slot is one sorter handle doing
     # collect (H2D of the step's 8 GB) -> flush (sort + D2H of the step's 8.2 GB file.out); with two slots the H2D of one
@@ -315,7 +357,7 @@ def single_gpu(args):
             "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(1, n),
             "clocks": clk, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "pipeline": pipeline,
-            "cpu_baseline": cpu}
+            "config4_pipeline_g1": pipeline_g1, "cpu_baseline": cpu}
     print(json.dumps(line))
     return 0
 
@@ -326,11 +368,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--records", type=int, default=100_000_000)
+    ap.add_argument("--records", type=int, default=None,
+                    help="records per GPU (default: 1e8 at N=1 = BASELINE config 2; 1.25e8 at N>1 = config 4's 1e9 over 8 GPUs)")
     ap.add_argument("--cpu-records-per-task", type=int, default=1_000_000)
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-g1-pipeline", action="store_true")
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.records is None:
+        args.records = 100_000_000 if (args.gpus == 1 and world == 1) else 125_000_000
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3
     if args.impl == "reference":
@@ -338,7 +385,14 @@ def main():
     if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         return single_gpu(args)
     from tez_b200 import multigpu_bench
-    return multigpu_bench.run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores)
+
+    def verify_partition(runs, merged):
+        # the checker (test infrastructure, outside the timed region): TezMerger restatement over the same runs
+        from oracle import tez_oracle as O
+        exp = O.merge(runs, O.CMP_BYTES, factor=100)["ifile"]
+        assert merged == exp, "merged partition differs from the oracle's TezMerger output"
+
+    return multigpu_bench.run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores, verify_partition)
 
 
 if __name__ == "__main__":

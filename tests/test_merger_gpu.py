@@ -215,6 +215,13 @@ def test_check_for_same_keys_and_writer_rle_grid(inputs_rle, dup_pct):
         ndup = per * dup_pct // 100
         keys += [keys[rng.randrange(per)] for _ in range(ndup // 2)]                 # duplicates inside the segment
         keys += [pool[rng.randrange(len(pool))] for _ in range(ndup - ndup // 2)]    # and (likely) across segments
+        if not inputs_rle:
+            # Unencoded duplicates INSIDE a segment whose key also lives in another segment make the reference's
+            # SAME/DIFF flags depend on which segment its heap happens to hold on top (Hadoop PriorityQueue tie order,
+            # "parity unpinned" in DESIGN.md 6); a producer only leaves duplicates unencoded when they are rare, and
+            # the device's canonical (segment, position) order cannot reproduce that history.  Keep them across
+            # segments only.
+            keys = list(set(keys))
         keys.sort()
         segs.append(O.write_ifile([(k, zlib.crc32(k).to_bytes(4, "big") * (1 + k[0] % 3)) for k in keys], rle=inputs_rle)[0])
     shared = set(k for _, k, _ in O.read_ifile(segs[0]) if k) & set(k for _, k, _ in O.read_ifile(segs[1]))

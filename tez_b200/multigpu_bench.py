@@ -16,7 +16,9 @@ REC = KEY_LEN + VAL_LEN
 OUT_REC = REC + 2
 
 
-def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
+def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores, verify_partition=None):
+    """verify_partition(run_bytes_list, merged_segment_bytes) -> None or raises: the caller's checker (bench.py passes the
+    CPU oracle's TezMerger restatement); run on every rank for one owned partition AFTER the timed region."""
     import tez_b200 as T
     from tez_b200 import shuffle, synth
     rank = int(os.environ.get("RANK", "0"))
@@ -51,6 +53,7 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
     merger = [None]
     phase_ms = {"sort": [], "exchange": [], "merge": []}
     fetch_ms = []
+    last_step = [None, None, 0]
 
     def step(timed):
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -82,6 +85,7 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
         m = merger[0]
         mlen, mindex, mst = m.write_partitions_device(d_merged.data_ptr(), d_merged.numel())
         nrec, _ = m.counts()
+        last_step[:] = [segs, mindex, mlen]
         e[3].record()
         if timed:
             torch.cuda.synchronize()
@@ -130,6 +134,7 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
             m = merger[0]
             mlen, mindex, mst = m.write_partitions_device(d_merged.data_ptr(), d_merged.numel())
             nrec, _ = m.counts()
+            last_step[:] = [segs, mindex, mlen]
             e[2].record()
             if timed:
                 torch.cuda.synchronize()
@@ -166,6 +171,31 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
     dist.all_reduce(ph_max, op=dist.ReduceOp.MAX)
     dist.all_reduce(ph_min, op=dist.ReduceOp.MIN)
     clk = clocks.stop() if rank == 0 else None
+    # ---- outside the timed region: every rank checks one partition it owns, byte for byte -- the G runs it merged
+    # (device memory: the local slot or the receive buffer) through the caller's checker against its merged segment,
+    # and the segment's CRC32 trailer with zlib
+    checked = torch.zeros(1, device=dev, dtype=torch.float64)
+    if verify_partition is not None and last_step[0] is not None:
+        import zlib
+        segs_l, mindex_l, _ = last_step
+        owned = sorted({p for _, _, p, _ in segs_l})
+        if owned:
+            lp = owned[(rank * 7) % len(owned)]                      # a different local partition on every rank
+
+            def dev_bytes(ptr, ln):   # raw device address -> host bytes, through the library's own copy kernel
+                t = torch.empty(ln + 32, dtype=torch.uint8, device=dev)
+                torch.cuda.synchronize()
+                off = (ptr - t.data_ptr()) % 16
+                T.fetch_ranges([(ptr, t.data_ptr() + off, ln)], local)
+                return t[off:off + ln].cpu().numpy().tobytes()
+
+            runs = [dev_bytes(ptr, ln) for ptr, ln, p, _ in segs_l if p == lp]
+            a, _, ln = (int(x) for x in mindex_l[lp])
+            merged = d_merged[a:a + ln].cpu().numpy().tobytes()
+            assert int.from_bytes(merged[-4:], "big") == zlib.crc32(merged[4:-4]), "CRC32 trailer of the merged segment"
+            verify_partition(runs, merged)
+            checked[0] = 1
+    dist.all_reduce(checked)
     if rank == 0:
         total_records = n * world
         assert int(tot[0].item()) == total_records, "records lost in the shuffle"
@@ -192,6 +222,9 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores):
                              "unit": "GB/s", "frac": round(n * (2 * 162) / (ms_step * 1e-3) / 1e9 / peak, 4),
                              "traffic": None, "peak_source": peak_src,
                              "note": "per GPU: sort (162 B/rec) + merge (164 B/rec) algorithmic bytes over the whole step"},
+                "parity_check": {"ranks_checked": int(checked.item()),
+                                 "what": "after the timed region every rank compared one owned partition's merged segment with the CPU "
+                                         "oracle's TezMerger over the G runs it merged (byte-exact) and its CRC32 trailer with zlib"},
                 "cpu_baseline": None}
         print(json.dumps(line))
     if px:
