@@ -208,22 +208,20 @@ def test_check_for_same_keys_and_writer_rle_grid(inputs_rle, dup_pct):
     checkForSameKeys off, isSameKey() is only what the input segments' own run-length encoding says."""
     rng = random.Random(1000 * dup_pct + inputs_rle)
     nseg, per = 5, 4000
-    pool = [rng.getrandbits(64).to_bytes(8, "big") for _ in range(nseg * per)]
+    # Two kinds of duplicates, kept apart on purpose: keys SHARED by several segments occur at most once per segment, and
+    # keys repeated INSIDE a segment are private to it.  When one key is both repeated inside a segment and present in
+    # another one, the reference's SAME/DIFF flags depend on which of the two segments its heap (Hadoop PriorityQueue,
+    # strict lessThan) happens to hold on top -- "parity unpinned" in DESIGN.md 6 -- and no canonical order reproduces it.
+    shared_pool = [b"S" + rng.getrandbits(56).to_bytes(7, "big") for _ in range(nseg * per // 2)]
     segs = []
     for s in range(nseg):
-        keys = [pool[rng.randrange(len(pool))] for _ in range(per)]
         ndup = per * dup_pct // 100
-        keys += [keys[rng.randrange(per)] for _ in range(ndup // 2)]                 # duplicates inside the segment
-        keys += [pool[rng.randrange(len(pool))] for _ in range(ndup - ndup // 2)]    # and (likely) across segments
-        if not inputs_rle:
-            # Unencoded duplicates INSIDE a segment whose key also lives in another segment make the reference's
-            # SAME/DIFF flags depend on which segment its heap happens to hold on top (Hadoop PriorityQueue tie order,
-            # "parity unpinned" in DESIGN.md 6); a producer only leaves duplicates unencoded when they are rare, and
-            # the device's canonical (segment, position) order cannot reproduce that history.  Keep them across
-            # segments only.
-            keys = list(set(keys))
+        mine = set(b"P" + bytes([s]) + rng.getrandbits(48).to_bytes(6, "big") for _ in range(per // 2))
+        keys = list(mine) + list(set(shared_pool[rng.randrange(len(shared_pool))] for _ in range(per // 2 + ndup)))
+        private = sorted(mine)
+        keys += [private[rng.randrange(len(private))] for _ in range(ndup)]          # repeats inside the segment
         keys.sort()
-        segs.append(O.write_ifile([(k, zlib.crc32(k).to_bytes(4, "big") * (1 + k[0] % 3)) for k in keys], rle=inputs_rle)[0])
+        segs.append(O.write_ifile([(k, zlib.crc32(k).to_bytes(4, "big") * (1 + k[1] % 3)) for k in keys], rle=inputs_rle)[0])
     shared = set(k for _, k, _ in O.read_ifile(segs[0]) if k) & set(k for _, k, _ in O.read_ifile(segs[1]))
     for check in (True, False):
         for writer_rle in (False, True):

@@ -108,8 +108,15 @@ def test_multi_spill_final_merge_with_duplicate_keys(tmp_path, dup_pct):
     rng = random.Random(dup_pct)
     nd = n * dup_pct // 100
     base = [bytes(r[:16]) for r in O.gen_c2(0, n - nd, seed=17).reshape(-1, 80)]
-    keys = base + [base[rng.randrange(len(base))] for _ in range(nd)]
-    rng.shuffle(keys)
+    # duplicates stay close to their originals (shuffled inside blocks of 500 records), so every spill sees the same
+    # duplicate fraction as the whole input: the RLE decision is per spill (SpanMerger.needsRLE of that spill's sort)
+    keys = []
+    for blk in range(0, len(base), 500):
+        part = base[blk:blk + 500]
+        part = part + [part[rng.randrange(len(part))] for _ in range(len(part) * nd // len(base))]
+        rng.shuffle(part)
+        keys += part
+    n = len(keys)
     recs = [(k, zlib.crc32(k).to_bytes(4, "big") * 16) for k in keys]
     conf = {"tez.runtime.key.class": BYTES_WRITABLE, "tez.runtime.key.comparator.class": TEZ_BYTES_COMPARATOR,
             "tez.runtime.io.sort.mb": 1}

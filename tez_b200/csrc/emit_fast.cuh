@@ -136,11 +136,8 @@ struct FastEmitParams {
 };
 
 // byte offset in kv of record ri's key: explicit array, arithmetic over the run table, or packed
-__device__ __forceinline__ uint64_t fast_source_offset(const Records &rec, uint32_t ri, uint32_t stride) {
-  if (rec.use_runs) {
-    uint32_t seg;
-    return run_record_off(rec.runs, ri, seg) + rec.runs.hdr_len;
-  }
+__device__ __forceinline__ uint64_t fast_source_offset(const Records &rec, uint32_t ri, uint32_t stride, uint32_t p) {
+  if (rec.use_runs) return run_record_off_p(rec.runs, p, ri) + rec.runs.hdr_len;   // p: the tile's partition
   return rec.key_off ? rec.key_off[ri] : (uint64_t)ri * stride;
 }
 
@@ -190,7 +187,7 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT_MIN_CTAS) k_emit_fast(
     if ((uint32_t)tid < td_next.nr) {
       const uint32_t ri = e.order[td_next.r0 + tid];
       s_idx[0][tid] = ri;
-      if (!ALIGNED) s_off[0][tid] = fast_source_offset(e.rec, ri, stride);
+      if (!ALIGNED) s_off[0][tid] = fast_source_offset(e.rec, ri, stride, td_next.p);
     }
   }
   uint32_t buf = 0;
@@ -257,7 +254,7 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT_MIN_CTAS) k_emit_fast(
     if (tile_n < fp.ntiles && (uint32_t)tid < td_next.nr) {
       const uint32_t ri = e.order[td_next.r0 + tid];
       s_idx[buf ^ 1u][tid] = ri;
-      if (!ALIGNED) s_off[buf ^ 1u][tid] = fast_source_offset(e.rec, ri, stride);
+      if (!ALIGNED) s_off[buf ^ 1u][tid] = fast_source_offset(e.rec, ri, stride, td_next.p);
     }
     // ---- framing: vint(klen) vint(vlen) in front of every record, segment header, EOF markers
     if ((uint32_t)tid < nr) {

@@ -90,11 +90,10 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast
   const uint32_t rec_size = e.rec_size, hdr_len = e.fixed_hdr_len, stride = fp.stride, cpr = fp.cpr;
   const TileDesc *__restrict__ tiles = fp.tiles;
   const bool use_runs = e.rec.use_runs;
-  auto source_offset = [&](uint32_t ri) -> uint64_t {
-    if (use_runs) {  // fixed-framing runs read in place: offset = f(segment table, index), no per-record array
-      uint32_t seg;
-      return run_record_off(e.rec.runs, ri, seg) + e.rec.runs.hdr_len;
-    }
+  auto source_offset = [&](uint32_t ri, uint32_t p) -> uint64_t {
+    // fixed-framing runs read in place: offset = f(segment table, index) -- the record lies in one of the few runs of
+    // the tile's partition p -- no per-record array
+    if (use_runs) return run_record_off_p(e.rec.runs, p, ri) + e.rec.runs.hdr_len;
     return key_off ? key_off[ri] : (uint64_t)ri * stride;
   };
 
@@ -150,22 +149,24 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast
   // ---- prologue: offsets of tiles 0 and 1 (order -> index -> offset, exposed once), record indices of tile 2,
   //      descriptors up to tile 3, gather of tile 0 in flight
   uint32_t nr0, fl0, nr1 = 0, fl1 = 0, nr2 = 0, ri2 = 0, r0_3 = 0, nr3 = 0;
+  uint32_t p2 = 0, p3 = 0;   // partitions of tiles N+2 / N+3 (run-table offsets)
   uint64_t abs0, abs1 = 0;
   {
     const TileDesc t0 = tiles[tile];
     nr0 = t0.nr; fl0 = t0.flags; abs0 = t0.abs0;
-    if ((uint32_t)tid < nr0) s_off[0][tid] = source_offset(e.order[t0.r0 + tid]);
+    if ((uint32_t)tid < nr0) s_off[0][tid] = source_offset(e.order[t0.r0 + tid], t0.p);
     if (tile + G < ntiles) {
       const TileDesc t1 = tiles[tile + G];
       nr1 = t1.nr; fl1 = t1.flags; abs1 = t1.abs0;
-      if ((uint32_t)tid < nr1) s_off[1][tid] = source_offset(e.order[t1.r0 + tid]);
+      if ((uint32_t)tid < nr1) s_off[1][tid] = source_offset(e.order[t1.r0 + tid], t1.p);
     }
     if (tile + 2 * (uint64_t)G < ntiles) {
       const TileDesc t2 = tiles[tile + 2 * (uint64_t)G];
       nr2 = t2.nr;
+      p2 = t2.p;
       if ((uint32_t)tid < nr2) ri2 = e.order[t2.r0 + tid];
     }
-    if (tile + 3 * (uint64_t)G < ntiles) { r0_3 = tiles[tile + 3 * (uint64_t)G].r0; nr3 = tiles[tile + 3 * (uint64_t)G].nr; }
+    if (tile + 3 * (uint64_t)G < ntiles) { r0_3 = tiles[tile + 3 * (uint64_t)G].r0; nr3 = tiles[tile + 3 * (uint64_t)G].nr; p3 = tiles[tile + 3 * (uint64_t)G].p; }
   }
   __syncthreads();
   issue_gather(nr0, s_off[0]);
@@ -183,14 +184,14 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast
 
     // ---- prefetches consumed at the end of this iteration: offsets of tile N+2, indices of tile N+3, descriptors
     uint64_t off2 = 0, abs2n = 0;
-    uint32_t ri3 = 0, r0_4 = 0, nr4 = 0, nr2n = 0, fl2n = 0;
+    uint32_t ri3 = 0, r0_4 = 0, nr4 = 0, nr2n = 0, fl2n = 0, p4 = 0;
     if (has2) {
-      if ((uint32_t)tid < nr2) off2 = source_offset(ri2);
+      if ((uint32_t)tid < nr2) off2 = source_offset(ri2, p2);
       const TileDesc *t2 = tiles + tile + 2 * (uint64_t)G;
       nr2n = t2->nr; fl2n = t2->flags; abs2n = t2->abs0;
     }
     if (has3 && (uint32_t)tid < nr3) ri3 = e.order[r0_3 + tid];
-    if (has4) { const TileDesc *t4 = tiles + tile + 4 * (uint64_t)G; r0_4 = t4->r0; nr4 = t4->nr; }
+    if (has4) { const TileDesc *t4 = tiles + tile + 4 * (uint64_t)G; r0_4 = t4->r0; nr4 = t4->nr; p4 = t4->p; }
 
     // ---- this tile's words (loaded during the previous iteration) -> pieces -> image; framing
 #pragma unroll
@@ -316,8 +317,8 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast
     asm volatile("" : "+r"(nr2n), "+r"(fl2n), "+l"(abs2n), "+r"(ri3), "+r"(r0_4), "+r"(nr4));
     nr0 = nr1; fl0 = fl1; abs0 = abs1;
     nr1 = nr2n; fl1 = fl2n; abs1 = abs2n;
-    nr2 = nr3; ri2 = ri3;
-    r0_3 = r0_4; nr3 = nr4;
+    nr2 = nr3; ri2 = ri3; p2 = p3;
+    r0_3 = r0_4; nr3 = nr4; p3 = p4;
   }
 }
 

@@ -5,9 +5,11 @@
 // order), and the merged stream is either iterated (TezRawKeyValueIterator) or written as one IFile segment
 // (TezMerger.writeFile, :215-245) with REPEAT_KEY run-length encoding of equal adjacent keys.
 #pragma once
+#include <algorithm>
 #include <vector>
 
 #include "sorter.cuh"
+#include "parse_windows.cuh"
 
 namespace tezgpu {
 
@@ -392,7 +394,8 @@ class Merger {
 
   explicit Merger(const tezgpu_conf &c) : pipe(pipe_conf(c)), fixed_klen(c.fixed_key_len), fixed_vlen(c.fixed_val_len) {}
 
-  DeviceBuffer d_run_off, d_run_base, d_run_part, d_flags;
+  DeviceBuffer d_run_off, d_run_base, d_run_part, d_run_pseg, d_flags;
+  std::vector<uint32_t> seg_orig;   // position in the partition-major list -> index in the caller's segment array
   bool arrays_ready = false;   // the per-record metadata arrays (d_koff ...) are filled (never in run-table mode unless asked)
   std::vector<uint64_t> h_counts, h_rec_base;
 
@@ -415,19 +418,27 @@ class Merger {
       }
     lo_addr &= ~(uintptr_t)15;
     bool any_header = false;
+    // Segments are kept partition-major (stable: the caller's order inside a partition is the merge's tie order): the
+    // records of one output partition then live in a handful of consecutive runs, which makes the run-table lookups of
+    // the stage / emit kernels a scan over <= G entries instead of a binary search over all segments.
+    seg_orig.resize(nseg);
+    for (uint32_t s = 0; s < nseg; s++) seg_orig[s] = s;
+    if (pipe.conf.num_partitions > 1)
+      std::stable_sort(seg_orig.begin(), seg_orig.end(), [&](uint32_t a, uint32_t b) { return in[a].partition < in[b].partition; });
     for (uint32_t s = 0; s < nseg; s++) {
-      TG_CHECK(in[s].data || in[s].len == 0, TEZGPU_E_INVALID, "null segment");
-      const bool hdr = in[s].flags & TEZGPU_SEG_HAS_HEADER;
+      const tezgpu_segment &sg = in[seg_orig[s]];
+      TG_CHECK(sg.data || sg.len == 0, TEZGPU_E_INVALID, "null segment");
+      const bool hdr = sg.flags & TEZGPU_SEG_HAS_HEADER;
       any_header |= hdr;
-      TG_CHECK(in[s].len >= (hdr ? 10u : 6u), TEZGPU_E_FORMAT, "IFile segment shorter than an empty segment");
-      segs[s].off = all_device ? (uint64_t)((uintptr_t)in[s].data - lo_addr) : off;
-      segs[s].len = in[s].len;
+      TG_CHECK(sg.len >= (hdr ? 10u : 6u), TEZGPU_E_FORMAT, "IFile segment shorter than an empty segment");
+      segs[s].off = all_device ? (uint64_t)((uintptr_t)sg.data - lo_addr) : off;
+      segs[s].len = sg.len;
       segs[s].body0 = hdr ? 4 : 0;
-      segs[s].body_end = in[s].len - 4;
-      segs[s].has_header = (hdr ? 1u : 0u) | ((hdr && (in[s].flags & TEZGPU_SEG_VERIFIED)) ? 2u : 0u);
-      segs[s].partition = in[s].partition;
-      TG_CHECK((int)in[s].partition < pipe.conf.num_partitions, TEZGPU_E_INVALID, "segment partition out of range");
-      off = align_up(off + in[s].len, 16);
+      segs[s].body_end = sg.len - 4;
+      segs[s].has_header = (hdr ? 1u : 0u) | ((hdr && (sg.flags & TEZGPU_SEG_VERIFIED)) ? 2u : 0u);
+      segs[s].partition = sg.partition;
+      TG_CHECK((int)sg.partition < pipe.conf.num_partitions, TEZGPU_E_INVALID, "segment partition out of range");
+      off = align_up(off + sg.len, 16);
     }
     if (all_device) {
       data = reinterpret_cast<const uint8_t *>(lo_addr);
@@ -437,9 +448,10 @@ class Merger {
       seg_bytes = off;
       d_data.ensure(off + 64);
       for (uint32_t s = 0; s < nseg; s++) {
-        if (!in[s].len) continue;
-        const bool dev = in[s].flags & TEZGPU_SEG_DEVICE;
-        TG_CUDA(cudaMemcpyAsync(d_data.as<uint8_t>() + segs[s].off, in[s].data, in[s].len,
+        const tezgpu_segment &sg = in[seg_orig[s]];
+        if (!sg.len) continue;
+        const bool dev = sg.flags & TEZGPU_SEG_DEVICE;
+        TG_CUDA(cudaMemcpyAsync(d_data.as<uint8_t>() + segs[s].off, sg.data, sg.len,
                                 dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
       }
       data = d_data.as<uint8_t>();
@@ -485,9 +497,9 @@ class Merger {
       int f[3] = {0, 0, 0};
       TG_CUDA(cudaMemcpyAsync(f, d_vflags, 12, cudaMemcpyDeviceToHost, st));
       TG_CUDA(cudaStreamSynchronize(st));
-      TG_CHECK(f[0] == 0, TEZGPU_E_FORMAT, "Not a valid ifile header (segment " + std::to_string(f[0] - 1) + ")");
+      TG_CHECK(f[0] == 0, TEZGPU_E_FORMAT, "Not a valid ifile header (segment " + std::to_string(f[0] ? seg_orig[f[0] - 1] : 0) + ")");
       TG_CHECK(f[1] == 0, TEZGPU_E_UNSUPPORTED, "compressed IFile segments are not supported on the device path");
-      TG_CHECK(f[2] == 0, TEZGPU_E_FORMAT, "IFile checksum mismatch in segment " + std::to_string(f[2] - 1));
+      TG_CHECK(f[2] == 0, TEZGPU_E_FORMAT, "IFile checksum mismatch in segment " + std::to_string(f[2] ? seg_orig[f[2] - 1] : 0));
     };
 
     // ---- records per segment
@@ -517,6 +529,12 @@ class Merger {
       std::vector<uint32_t> rbase(nseg + 1), rpart(nseg);
       for (uint32_t s = 0; s < nseg; s++) { roff[s] = segs[s].off + segs[s].body0; rbase[s] = (uint32_t)h_rec_base[s]; rpart[s] = segs[s].partition; }
       rbase[nseg] = (uint32_t)n;
+      const int P = pipe.conf.num_partitions;
+      std::vector<uint32_t> pseg((size_t)P + 1, 0);
+      for (uint32_t s = 0; s < nseg; s++) pseg[segs[s].partition + 1]++;
+      for (int p = 0; p < P; p++) pseg[p + 1] += pseg[p];
+      d_run_pseg.ensure(((size_t)P + 1) * 4);
+      TG_CUDA(cudaMemcpyAsync(d_run_pseg.p, pseg.data(), ((size_t)P + 1) * 4, cudaMemcpyHostToDevice, st));
       d_run_off.ensure((size_t)nseg * 8); d_run_base.ensure((size_t)(nseg + 1) * 4); d_run_part.ensure((size_t)nseg * 4);
       TG_CUDA(cudaMemcpyAsync(d_run_off.p, roff.data(), (size_t)nseg * 8, cudaMemcpyHostToDevice, st));
       TG_CUDA(cudaMemcpyAsync(d_run_base.p, rbase.data(), (size_t)(nseg + 1) * 4, cudaMemcpyHostToDevice, st));
@@ -534,6 +552,7 @@ class Merger {
       r.runs.seg_off = d_run_off.as<uint64_t>();
       r.runs.rec_base = d_run_base.as<uint32_t>();
       r.runs.seg_part = d_run_part.as<uint32_t>();
+      r.runs.part_seg0 = d_run_pseg.as<uint32_t>();
       r.runs.nseg = nseg;
       r.runs.rec_size = rs;
       r.runs.hdr_len = vint_size_u32(fixed_klen) + vint_size_u32(fixed_vlen);
@@ -632,8 +651,98 @@ class Merger {
     arrays_ready = true;
   }
 
+  // ---- parallel parser (parse_windows.cuh): every window of every segment walks at once, entries iterate to the fixed
+  // point.  Returns false when the rounds cap is hit (adversarial bytes): the caller falls back to the sequential walker.
+  DeviceBuffer d_pwseg, d_entry[2], d_wcount, d_wbase, d_wlast, d_carry, d_pwflags;
+  int parse_rounds = 0;
+  bool parse_parallel(uint32_t nseg) {
+    cudaStream_t st = pipe.stream;
+    std::vector<PwSeg> ps(nseg);
+    uint64_t nw = 0;
+    for (uint32_t s = 0; s < nseg; s++) {
+      ps[s].off = segs[s].off; ps[s].len = segs[s].len; ps[s].body0 = segs[s].body0; ps[s].body_end = segs[s].body_end;
+      ps[s].win0 = (uint32_t)nw;
+      ps[s].nwin = (uint32_t)std::max<uint64_t>(1, div_up(segs[s].body_end - segs[s].body0, PW_WINDOW));
+      ps[s].partition = segs[s].partition;
+      ps[s].pad = 0;
+      nw += ps[s].nwin;
+    }
+    TG_CHECK(nw < (1ull << 31), TEZGPU_E_INVALID, "segments too large for one merge");
+    const uint32_t nwin = (uint32_t)nw;
+    d_pwseg.ensure((size_t)nseg * sizeof(PwSeg));
+    for (int b = 0; b < 2; b++) d_entry[b].ensure((size_t)nwin * 8);
+    d_wcount.ensure((size_t)nwin * 4);
+    d_wbase.ensure(((size_t)nwin + 2) * 8);
+    d_wlast.ensure((size_t)nwin * 16);
+    d_pwflags.ensure(64);
+    TG_CUDA(cudaMemcpyAsync(d_pwseg.p, ps.data(), (size_t)nseg * sizeof(PwSeg), cudaMemcpyHostToDevice, st));
+    const uint32_t grid = (uint32_t)div_up(nwin, PW_THREADS);
+    PwArrays none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // guess round: every window publishes the exit of the first candidate walk that survives it
+    k_parse_windows<0><<<grid, PW_THREADS, 0, st>>>(data, d_pwseg.as<PwSeg>(), nseg, nwin, nullptr, d_entry[0].as<uint64_t>(), nullptr, nullptr,
+                                                    nullptr, d_pwflags.as<int>(), nullptr, nullptr, none);
+    launches++;
+    int cur = 0, flags[4] = {1, 0, 0, 0};
+    parse_rounds = 0;
+    while (flags[0] && parse_rounds < (int)PW_MAX_ROUNDS) {
+      TG_CUDA(cudaMemsetAsync(d_pwflags.p, 0, 64, st));
+      k_parse_windows<1><<<grid, PW_THREADS, 0, st>>>(data, d_pwseg.as<PwSeg>(), nseg, nwin, d_entry[cur].as<uint64_t>(),
+                                                      d_entry[cur ^ 1].as<uint64_t>(), d_wcount.as<uint32_t>(), d_wlast.as<uint64_t>(),
+                                                      nullptr, d_pwflags.as<int>(), nullptr, nullptr, none);
+      TG_CUDA(cudaGetLastError());
+      TG_CUDA(cudaMemcpyAsync(flags, d_pwflags.p, 16, cudaMemcpyDeviceToHost, st));
+      TG_CUDA(cudaStreamSynchronize(st));
+      launches++;
+      parse_rounds++;
+      cur ^= 1;
+    }
+    if (flags[0]) return false;
+    cur ^= 1;  // the entries the last (unchanged) round walked from
+    TG_CHECK(flags[1] == 0, TEZGPU_E_FORMAT, "malformed IFile segment " + std::to_string(flags[1] ? seg_orig[flags[1] - 1] : 0));
+    // ---- record offsets of every window, totals
+    const uint32_t nblk = (uint32_t)div_up(nwin, SCAN_TILE);
+    pipe.blk.ensure(((size_t)nblk + 2) * 8);
+    k_sum_u32_blocks<<<nblk, SCAN_THREADS, 0, st>>>(d_wcount.as<uint32_t>(), nwin, pipe.blk.as<uint64_t>());
+    k_scan_block_sums<<<1, 1024, 0, st>>>(pipe.blk.as<uint64_t>(), nblk);
+    k_scan_u32_apply<<<nblk, SCAN_THREADS, 0, st>>>(d_wcount.as<uint32_t>(), nwin, pipe.blk.as<uint64_t>(), d_wbase.as<uint64_t>());
+    d_counts.ensure((size_t)(nseg + 1) * 16);
+    k_parse_seg_counts<<<(uint32_t)div_up(nseg, 128), 128, 0, st>>>(d_pwseg.as<PwSeg>(), nseg, d_wbase.as<uint64_t>(), d_counts.as<uint64_t>());
+    launches += 4;
+    uint64_t total = 0;
+    TG_CUDA(cudaMemcpyAsync(&total, d_wbase.as<uint64_t>() + nwin, 8, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaMemcpyAsync(h_counts.data(), d_counts.p, (size_t)nseg * 8, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaStreamSynchronize(st));
+    n = total;
+    TG_CHECK(n <= RADIX_MAX_N, TEZGPU_E_INVALID, "more than 2^30-1 records in one merge");
+    uint64_t acc = 0;
+    for (uint32_t s = 0; s < nseg; s++) { h_rec_base[s] = acc; acc += h_counts[s]; }
+    h_rec_base[nseg] = acc;
+    d_koff.ensure((size_t)(n ? n : 1) * 8); d_voff.ensure((size_t)(n ? n : 1) * 8);
+    d_klen.ensure((size_t)(n ? n : 1) * 4); d_vlen.ensure((size_t)(n ? n : 1) * 4); d_tag.ensure((size_t)(n ? n : 1) * 4); d_part.ensure((size_t)(n ? n : 1) * 4);
+    PwArrays pa{d_koff.as<uint64_t>(), d_voff.as<uint64_t>(), d_klen.as<uint32_t>(), d_vlen.as<uint32_t>(), d_tag.as<uint32_t>(), d_part.as<int32_t>()};
+    d_carry.ensure((size_t)nwin * 16);
+    k_parse_carry<<<grid, PW_THREADS, 0, st>>>(d_pwseg.as<PwSeg>(), nseg, nwin, d_entry[cur].as<uint64_t>(), d_wlast.as<uint64_t>(), d_carry.as<uint64_t>());
+    const uint64_t *carry = d_carry.as<uint64_t>();
+    launches++;
+    TG_CUDA(cudaMemsetAsync(d_pwflags.p, 0, 64, st));
+    unsigned long long *d_kv_total = reinterpret_cast<unsigned long long *>(d_pwflags.as<int>() + 8);
+    k_parse_windows<2><<<grid, PW_THREADS, 0, st>>>(data, d_pwseg.as<PwSeg>(), nseg, nwin, d_entry[cur].as<uint64_t>(), nullptr, nullptr, nullptr,
+                                                       d_kv_total, d_pwflags.as<int>(), d_wbase.as<uint64_t>(), carry, pa);
+    launches++;
+    TG_CUDA(cudaGetLastError());
+    unsigned long long kvb = 0;
+    TG_CUDA(cudaMemcpyAsync(flags, d_pwflags.p, 16, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaMemcpyAsync(&kvb, d_kv_total, 8, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaStreamSynchronize(st));
+    TG_CHECK(flags[1] == 0, TEZGPU_E_FORMAT, "malformed IFile segment " + std::to_string(flags[1] ? seg_orig[flags[1] - 1] : 0));
+    kv_bytes = kvb;
+    return true;
+  }
+
   void open_general_reparse(uint32_t nseg, std::vector<uint64_t> &counts, std::vector<uint64_t> &rec_base) {
     cudaStream_t st = pipe.stream;
+    static const bool serial_only = getenv("TEZGPU_PARSE_SERIAL") && atoi(getenv("TEZGPU_PARSE_SERIAL")) != 0;
+    if (!serial_only && parse_parallel(nseg)) return;
     int *d_bad = pipe.d_error();
     ParseArrays pa{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     k_parse_segments<false><<<(uint32_t)div_up(nseg, PARSE_WARPS), PARSE_WARPS * 32, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, d_counts.as<uint64_t>(),
@@ -642,7 +751,7 @@ class Merger {
     TG_CUDA(cudaMemcpyAsync(counts.data(), d_counts.p, (size_t)nseg * 16, cudaMemcpyDeviceToHost, st));
     TG_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
     TG_CUDA(cudaStreamSynchronize(st));
-    TG_CHECK(bad == 0, TEZGPU_E_FORMAT, "malformed IFile segment " + std::to_string(bad - 1));
+    TG_CHECK(bad == 0, TEZGPU_E_FORMAT, "malformed IFile segment " + std::to_string(bad ? seg_orig[bad - 1] : 0));
     n = 0;
     kv_bytes = 0;
     for (uint32_t s = 0; s < nseg; s++) { rec_base[s] = n; n += counts[s]; kv_bytes += counts[nseg + s]; }

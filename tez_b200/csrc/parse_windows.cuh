@@ -1,0 +1,270 @@
+// parse_windows.cuh -- parallel IFile parser for the reduce side (IFile.Reader semantics, SORT/IFile.java:877-1000).
+//
+// An IFile body is a chain: the position of record i+1 is only known once the vint lengths of record i are decoded,
+// and the format has no sync markers.  The walker of merger.cuh follows that chain with ONE lane per segment
+// (2.7 M dependent steps for a 64 MiB segment of 25-byte records).  Here every segment body is cut into windows of
+// PW_WINDOW bytes and ALL windows walk at once; a window publishes where its walk LEFT it (position + reader state),
+// which is the next window's entry.  Iterating
+//        entry_{t+1}[w+1] = exit( walk of window w from entry_t[w] ),      entry[first window] = body start,
+// reaches the fixed point after at most (#windows) rounds by induction (window w is exact after w rounds), and the
+// loop stops when a round changes no entry: then every entry is the true one, so that round's record counts -- and any
+// malformed record it met -- are the sequential reader's.  EXACTNESS never depends on the guesses below; only the number
+// of rounds does.
+//
+// Guess round: a walk started at a wrong byte usually dies within a few records (a byte decoded as a negative or huge
+// length), and one that survives falls into step with the true chain (from the first shared (position, state) on two
+// walks are identical).  So every window first tries candidate starts ws, ws+1, ... in both reader states until a walk
+// survives to the window's end, and publishes that walk's exit.  Measured on the CPU emulation (text keys, word-count
+// records, run-length encoded small records, 32 KiB windows): every window's exit is already exact after the guess
+// round, the first counting round confirms it (2 rounds).  Inputs where wrong walks survive without ever meeting the
+// true chain (multi-window run-length runs, records of random bytes larger than a window) converge one window per
+// round: after PW_MAX_ROUNDS the merger falls back to the sequential walker.
+//
+// Cost per round: every body byte is read once; typical total = guess + 1 counting + 1 emitting round.
+#pragma once
+#include "common.cuh"
+
+namespace tezgpu {
+
+struct SegDesc;  // merger.cuh
+
+constexpr uint32_t PW_WINDOW = 32768;
+constexpr uint32_t PW_MAX_TRIES = 2048;   // candidate start offsets per window in the guess round
+constexpr int PW_THREADS = 128;
+constexpr uint64_t PW_EOF = ~0ull;        // the reader met the EOF markers before this window
+constexpr uint64_t PW_BAD = ~0ull - 1;    // the walk that produced this entry met a malformed record
+constexpr uint32_t PW_MAX_ROUNDS = 6;
+
+struct PwSeg {
+  uint64_t off;        // segment start in the data buffer
+  uint64_t len;        // segment bytes
+  uint64_t body0;      // first body byte (4 with header, 0 in-memory)
+  uint64_t body_end;   // len - 4
+  uint32_t win0;       // first window of the segment in the global window list
+  uint32_t nwin;
+  uint32_t partition;
+  uint32_t pad;
+};
+
+// segment of window w: last s with segs[s].win0 <= w (segments are listed in window order; every segment has >= 1 window)
+__device__ __forceinline__ uint32_t pw_seg_of(const PwSeg *__restrict__ segs, uint32_t nseg, uint32_t w) {
+  uint32_t lo = 0, hi = nseg;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(&segs[mid].win0) <= w) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// per-segment record counts from the per-window offsets: counts[s] = wbase[win0 + nwin] - wbase[win0]
+__global__ void k_parse_seg_counts(const PwSeg *__restrict__ segs, uint32_t nseg, const uint64_t *__restrict__ wbase,
+                                   uint64_t *__restrict__ counts) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < nseg) counts[s] = wbase[segs[s].win0 + segs[s].nwin] - wbase[segs[s].win0];
+}
+
+// 8 bytes of the segment at offset pos (little endian); bytes past the segment read as zero.  fast: two aligned loads
+__device__ __forceinline__ uint64_t pw_load8(const uint8_t *__restrict__ seg, uint64_t pos, uint64_t seg_len) {
+  if (pos + 16 <= seg_len) {
+    const uintptr_t a = (uintptr_t)(seg + pos);
+    const uint32_t sh = (uint32_t)(a & 7u);
+    const uint64_t *q = reinterpret_cast<const uint64_t *>(a - sh);
+    const uint64_t x = __ldg(q);
+    if (sh == 0) return x;
+    const uint64_t y = __ldg(q + 1);
+    return (x >> (8u * sh)) | (y << (64u - 8u * sh));
+  }
+  uint64_t v = 0;
+  for (uint32_t b = 0; b < 8; b++)
+    if (pos + b < seg_len) v |= (uint64_t)seg[pos + b] << (8u * b);
+  return v;
+}
+
+// hadoop WritableUtils.readVLong at pos (bounded by end); false = runs past `end`
+__device__ __forceinline__ bool pw_vlong(const uint8_t *__restrict__ seg, uint64_t seg_len, uint64_t &pos, uint64_t end,
+                                         int64_t &out) {
+  if (pos >= end) return false;
+  const uint64_t x = pw_load8(seg, pos, seg_len);
+  const int8_t first = (int8_t)(x & 0xFF);
+  if (first >= -112) { out = first; pos += 1; return true; }
+  const int len = vint_decode_size((uint8_t)first);
+  if (pos + (uint64_t)len > end) return false;
+  uint64_t v = 0;
+  if (len <= 8) {
+    for (int i = 1; i < len; i++) v = (v << 8) | ((x >> (8 * i)) & 0xFF);
+  } else {  // 9-byte vlong: the last byte lies outside the 8-byte window
+    for (int i = 1; i < 8; i++) v = (v << 8) | ((x >> (8 * i)) & 0xFF);
+    v = (v << 8) | seg[pos + 8];
+  }
+  const bool neg = first < -120;   // (first >= -112 handled above)
+  out = neg ? (int64_t)~v : (int64_t)v;
+  pos += (uint64_t)len;
+  return true;
+}
+
+struct PwArrays {
+  uint64_t *key_off;
+  uint64_t *val_off;
+  uint32_t *key_len;
+  uint32_t *val_len;
+  uint32_t *tag;  // (segment << 1) | read as SAME_KEY (run-length encoded in the input)
+  int32_t *partition;
+};
+
+struct PwWalk {
+  uint64_t exit_v;      // (pos << 1) | state on leaving the window, PW_EOF, PW_BAD
+  uint32_t n;           // records that start in the window
+  uint64_t lk_off, lk_len;  // last full key seen (segment offset, length); lk_off = ~0 when none
+  uint64_t bytes;       // EMIT: key + value bytes
+};
+
+// the sequential reader over one window, from entry e
+template <bool EMIT>
+__device__ __forceinline__ PwWalk pw_walk(const uint8_t *__restrict__ seg, const PwSeg &sd, uint32_t s, uint64_t wend, bool last_win,
+                                          uint64_t e, uint64_t base, uint64_t carry_off, uint64_t carry_len, const PwArrays &out) {
+  PwWalk r;
+  r.exit_v = e;
+  r.n = 0;
+  r.lk_off = ~0ull;
+  r.lk_len = 0;
+  r.bytes = 0;
+  if (e == PW_EOF || e == PW_BAD) return r;
+  uint64_t pos = e >> 1;
+  int state = (int)(e & 1u);        // 1: the previous record was a repeat (cur_klen == -2 in the walker of merger.cuh)
+  // the key a repeat at the start of this window refers to: the last full key before the window (a window may begin
+  // inside a run-length encoded run, or with the run's RLE marker right after the key)
+  uint64_t orig_koff = carry_off, orig_klen = carry_len;
+  bool have_key = EMIT && carry_off != ~0ull;
+  int status = 0;                   // 0 running, 1 EOF, 2 malformed
+  // records that START inside this window belong to it; the last window also owns whatever lies up to the body end
+  while (pos < wend || last_win) {
+    uint64_t p2 = pos;
+    int64_t kl = 0, vl = 0;
+    bool ok;
+    if (state == 1) {  // a value length, or V_END_MARKER followed by both lengths
+      ok = pw_vlong(seg, sd.len, p2, sd.body_end, vl);
+      kl = -2;
+      if (ok && vl == -3) { ok = pw_vlong(seg, sd.len, p2, sd.body_end, kl); if (ok) ok = pw_vlong(seg, sd.len, p2, sd.body_end, vl); }
+    } else {
+      ok = pw_vlong(seg, sd.len, p2, sd.body_end, kl);
+      if (ok) ok = pw_vlong(seg, sd.len, p2, sd.body_end, vl);
+    }
+    if (!ok) { status = 2; break; }
+    if (kl == -1 && vl == -1) { status = 1; break; }                   // EOF markers
+    if ((kl != -2 && kl < 0) || vl < 0 || kl > 0x7fffffffll || vl > 0x7fffffffll) { status = 2; break; }
+    uint64_t q = p2;
+    if (kl != -2) {
+      if (q + (uint64_t)kl > sd.body_end) { status = 2; break; }
+      orig_koff = q;
+      orig_klen = (uint64_t)kl;
+      have_key = true;
+      r.lk_off = q;
+      r.lk_len = (uint64_t)kl;
+      q += (uint64_t)kl;
+    } else if (EMIT && !have_key) { status = 2; break; }                // a repeat needs a previous key
+    if (q + (uint64_t)vl > sd.body_end) { status = 2; break; }
+    if (EMIT) {
+      const uint64_t rr = base + r.n;
+      out.key_off[rr] = sd.off + orig_koff;
+      out.val_off[rr] = sd.off + q;
+      out.key_len[rr] = (uint32_t)orig_klen;
+      out.val_len[rr] = (uint32_t)vl;
+      out.tag[rr] = (s << 1) | (kl == -2 ? 1u : 0u);
+      out.partition[rr] = (int32_t)sd.partition;
+      r.bytes += orig_klen + (uint64_t)vl;
+    }
+    r.n++;
+    pos = q + (uint64_t)vl;
+    state = (kl == -2) ? 1 : 0;
+  }
+  if (status == 1) r.exit_v = PW_EOF;
+  else if (status == 2) r.exit_v = PW_BAD;
+  else r.exit_v = (pos << 1) | (uint64_t)state;
+  return r;
+}
+
+// One thread per window.
+//   MODE 0  guess round: first windows walk from the body start, every other window from the first candidate start
+//           (offset, reader state) whose walk survives to the window's end; publishes the exit as the next entry.
+//   MODE 1  counting round: walks from entry_in, publishes the exit, sets flags[0] when it differs from the entry the
+//           next window used, records the window's record count and its last full key.
+//   MODE 2  emitting round: entries are final; writes the per-record metadata at rec_base[w]...
+template <int MODE>
+__global__ void __launch_bounds__(PW_THREADS)
+    k_parse_windows(const uint8_t *__restrict__ data, const PwSeg *__restrict__ segs, uint32_t nseg,
+                    uint32_t nwin_total, const uint64_t *__restrict__ entry_in, uint64_t *__restrict__ entry_out,
+                    uint32_t *__restrict__ wcount, uint64_t *__restrict__ wlastkey /*[2*nwin]: off, len*/,
+                    unsigned long long *__restrict__ kv_total, int *__restrict__ flags /*[0] changed, [1] bad*/,
+                    const uint64_t *__restrict__ rec_base, const uint64_t *__restrict__ carry /*[2*nwin]*/, PwArrays out) {
+  constexpr bool EMIT = MODE == 2;
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t my_bytes = 0;
+  if (w < nwin_total) {
+    const uint32_t s = pw_seg_of(segs, nseg, w);
+    const PwSeg sd = segs[s];
+    const uint8_t *__restrict__ seg = data + sd.off;
+    const uint32_t k = w - sd.win0;
+    const uint64_t ws = sd.body0 + (uint64_t)k * PW_WINDOW;
+    const uint64_t wend = min(sd.body_end, ws + PW_WINDOW);
+    const bool last_win = (k + 1 == sd.nwin);
+    PwWalk r;
+    if (MODE == 0 && k > 0) {
+      r.exit_v = PW_BAD;
+      for (uint32_t o = 0; o < PW_MAX_TRIES && ws + o < wend && r.exit_v == PW_BAD; o++)
+        for (uint64_t st = 0; st < 2 && r.exit_v == PW_BAD; st++)
+          r = pw_walk<false>(seg, sd, s, wend, last_win, ((ws + o) << 1) | st, 0, ~0ull, 0, out);
+    } else {
+      const uint64_t e = (k == 0) ? (sd.body0 << 1) : entry_in[w];
+      r = pw_walk<EMIT>(seg, sd, s, wend, last_win, e, EMIT ? rec_base[w] : 0, EMIT ? carry[2 * (uint64_t)w] : ~0ull,
+                        EMIT ? carry[2 * (uint64_t)w + 1] : 0, out);
+    }
+    if (MODE == 0) {
+      if (!last_win) entry_out[w + 1] = r.exit_v;
+      if (k == 0) entry_out[w] = sd.body0 << 1;
+    } else if (MODE == 1) {
+      wcount[w] = r.n;
+      wlastkey[2 * (uint64_t)w] = r.lk_off;
+      wlastkey[2 * (uint64_t)w + 1] = r.lk_len;
+      if (!last_win) {
+        if (entry_in[w + 1] != r.exit_v) flags[0] = 1;
+        entry_out[w + 1] = r.exit_v;
+      } else if (r.exit_v != PW_EOF) {
+        // the stream must end with the EOF markers (only meaningful in the round that changed nothing: the host reads
+        // flags[1] from that round alone)
+        atomicMax(flags + 1, (int)s + 1);
+      }
+      if (k == 0) entry_out[w] = sd.body0 << 1;
+      if (r.exit_v == PW_BAD) atomicMax(flags + 1, (int)s + 1);
+    } else {
+      if (r.exit_v == PW_BAD) atomicMax(flags + 1, (int)s + 1);
+      my_bytes = r.bytes;
+    }
+  }
+  if (EMIT) {
+    // key + value bytes of the merged stream: warp-reduce, one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_bytes += __shfl_xor_sync(0xffffffffu, my_bytes, o);
+    if ((threadIdx.x & 31) == 0 && my_bytes) atomicAdd(kv_total, (unsigned long long)my_bytes);
+  }
+}
+
+// the last full key before every window (a repeat at a window's start refers to it): that of the nearest earlier
+// window of the same segment that saw one
+__global__ void k_parse_carry(const PwSeg *__restrict__ segs, uint32_t nseg, uint32_t nwin_total,
+                              const uint64_t *__restrict__ entry, const uint64_t *__restrict__ wlastkey, uint64_t *__restrict__ carry) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwin_total) return;
+  uint64_t off = ~0ull, len = 0;
+  const uint64_t e = entry[w];
+  if (e != PW_EOF && e != PW_BAD) {
+    const uint32_t w0 = segs[pw_seg_of(segs, nseg, w)].win0;
+    for (uint32_t v = w; v > w0;) {
+      v--;
+      if (wlastkey[2 * (uint64_t)v] != ~0ull) { off = wlastkey[2 * (uint64_t)v]; len = wlastkey[2 * (uint64_t)v + 1]; break; }
+    }
+  }
+  carry[2 * (uint64_t)w] = off;
+  carry[2 * (uint64_t)w + 1] = len;
+}
+
+}  // namespace tezgpu

@@ -454,7 +454,11 @@ class SortPipeline {
     if (tiles) {
       if (fast_emit) {
         int per_sm = 0;
-        static const bool use_tma = !(getenv("TEZGPU_EMIT_TMA") && atoi(getenv("TEZGPU_EMIT_TMA")) == 0);
+        // opt-in (TEZGPU_EMIT_TMA=1): byte-exact (68 GPU parity tests), but measured 15.4 ms against 5.45 ms for the
+        // register-staged kernel on 1e8 records -- the bulk-copy gather itself is as fast as the LDG gather
+        // (tools/bench_gather.cu: 4.4 ms either way, the memory system's rate for random 80-byte reads), the warp-divergent
+        // chunk assembly of the consumers is what costs (profiles/README.md, round 2)
+        static const bool use_tma = getenv("TEZGPU_EMIT_TMA") && atoi(getenv("TEZGPU_EMIT_TMA")) != 0;
         if (fast_aligned && use_tma && emit_tma_fits(e.recs_per_tile, stride)) {
           // gather by the bulk-copy engine into a shared-memory ring, chunks assembled straight from the staged
           // records (emit_tma.cuh); TEZGPU_EMIT_TMA=0 selects the register-staged kernels below

@@ -18,6 +18,7 @@ struct RunTable {
   const uint64_t *seg_off;    // [nseg] offset in kv of the first record (its framing bytes) of every segment
   const uint32_t *rec_base;   // [nseg + 1] first merge record index of every segment
   const uint32_t *seg_part;   // [nseg] output partition of every segment
+  const uint32_t *part_seg0;  // [P + 1] segments are listed partition-major: partition p owns [part_seg0[p], part_seg0[p+1])
   uint32_t nseg;
   uint32_t rec_size;          // framing + key + value bytes
   uint32_t hdr_len;           // framing bytes: vint(klen) vint(vlen)
@@ -33,9 +34,20 @@ __device__ __forceinline__ uint32_t run_of(const RunTable &t, uint32_t i) {
   }
   return lo;
 }
+// the same when the record's partition is known: its segment is one of the few runs of that partition
+__device__ __forceinline__ uint32_t run_of_in_partition(const RunTable &t, uint32_t p, uint32_t i) {
+  uint32_t seg = __ldg(t.part_seg0 + p);
+  const uint32_t end = __ldg(t.part_seg0 + p + 1);
+  while (seg + 1 < end && i >= __ldg(t.rec_base + seg + 1)) seg++;
+  return seg;
+}
 // byte offset in kv of record i's framing bytes
 __device__ __forceinline__ uint64_t run_record_off(const RunTable &t, uint32_t i, uint32_t &seg) {
   seg = run_of(t, i);
+  return __ldg(t.seg_off + seg) + (uint64_t)(i - __ldg(t.rec_base + seg)) * t.rec_size;
+}
+__device__ __forceinline__ uint64_t run_record_off_p(const RunTable &t, uint32_t p, uint32_t i) {
+  const uint32_t seg = run_of_in_partition(t, p, i);
   return __ldg(t.seg_off + seg) + (uint64_t)(i - __ldg(t.rec_base + seg)) * t.rec_size;
 }
 
@@ -117,8 +129,13 @@ __global__ void __launch_bounds__(256) k_stage(Records r, uint32_t *__restrict__
       uint32_t klen, vlen;
       int32_t run_part = 0;
       if (r.fixed && r.use_runs) {
-        uint32_t seg;
-        const uint64_t roff = run_record_off(r.runs, i, seg);
+        // consecutive records of a warp sit in the same run or the next few: one binary search per warp, lanes walk on
+        const unsigned am = __activemask();
+        const int leader = __ffs(am) - 1;
+        uint32_t seg = (int)(threadIdx.x & 31) == leader ? run_of(r.runs, i) : 0u;
+        seg = __shfl_sync(am, seg, leader);
+        while (seg + 1 < r.runs.nseg && i >= __ldg(r.runs.rec_base + seg + 1)) seg++;
+        const uint64_t roff = __ldg(r.runs.seg_off + seg) + (uint64_t)(i - __ldg(r.runs.rec_base + seg)) * r.runs.rec_size;
         koff = roff + r.runs.hdr_len;
         klen = r.klen;
         vlen = r.vlen;
