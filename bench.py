@@ -362,6 +362,98 @@ def single_gpu(args):
     return 0
 
 
+def config3(args):
+    """BASELINE config 3: k-way TezMerger of sorted spill segments with variable-length Text keys on one GPU.
+    Inputs: --c3-segments IFile segments of --c3-segment-mb MiB (SURVEY 8d generator: words from a 2^24-id space, length
+    U[4,24], 8-byte value = f(word), every word at most once per segment), resident in HBM when the timed region starts.
+    A step = tezgpu_merge_reopen (header / checksum verification, parallel parse, merge) + tezgpu_merge_write_ifile_device
+    (TezMerger.writeFile with REPEAT_KEY run-length encoding, CRC32)."""
+    import zlib
+    import numpy as np
+    import torch
+    import tez_b200 as T
+    from oracle import tez_oracle as O      # generator + checker + CPU arm (test infrastructure, never the product path)
+    nseg, seg_bytes = args.c3_segments, args.c3_segment_mb << 20
+    cores = min(host_cores(), 128)
+    t0 = time.perf_counter()
+    segs, nrec = O.gen_c3_segments(nseg, seg_bytes, seed=3, threads=cores)
+    t_gen = time.perf_counter() - t0
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    offs, total = [], 0
+    for a in segs:
+        offs.append(total)
+        total = (total + a.size + 15) // 16 * 16
+    d_in = torch.empty(total + 64, dtype=torch.uint8, device=dev)
+    for a, o in zip(segs, offs):
+        d_in[o:o + a.size].copy_(torch.from_numpy(a))
+    torch.cuda.synchronize()
+    in_bytes = sum(a.size for a in segs)
+    kv_in = in_bytes - 10 * nseg - 2 * sum(nrec)          # segment = 10 framing bytes + records of 2 vint bytes + key + value
+    seg_list = [(d_in.data_ptr() + o, a.size) for a, o in zip(segs, offs)]
+    m = T.GpuMerger(seg_list, comparator=T.CMP_TEXT, device=0, device_ptrs=True)
+    bound = m.output_bound()
+    d_out = torch.empty(bound + 64, dtype=torch.uint8, device=dev)
+
+    def step():
+        m.reopen(seg_list)
+        return m.write_ifile_device(d_out.data_ptr(), bound)
+
+    for _ in range(max(1, args.warmup)):
+        raw, part, st = step()
+    clocks = ClockSampler(0)
+    clocks.start()
+    torch.cuda.synchronize()
+    times, launches = [], 0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        raw, part, st = step()
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+        launches += st["kernel_launches"]
+    clk = clocks.stop()
+    ms_step = sum(times) / len(times) * 1e3
+    records, kv_bytes = m.counts()
+    assert records == sum(nrec) and kv_bytes == kv_in
+    value = kv_bytes / (ms_step * 1e-3) / 1e9
+    peak, peak_src = hbm_peak()
+    algo = in_bytes + part
+    # ---- parity, outside the timed region: CRC32 trailer with zlib over the whole output; byte-exact against the CPU
+    # oracle's TezMerger on a bounded sample of the same segments (which is also the CPU arm)
+    out = d_out[:part].cpu().numpy()
+    crc_ok = int.from_bytes(out[-4:].tobytes(), "big") == zlib.crc32(out[4:-4])
+    sample = max(2, min(nseg, args.c3_cpu_segments))
+    exp, n_cpu, secs = O.merge_ifile(segs[:sample], O.CMP_TEXT, factor=100)
+    m.reopen(seg_list[:sample])
+    raw_s, part_s, _ = m.write_ifile_device(d_out.data_ptr(), bound)
+    got = d_out[:part_s].cpu().numpy()
+    bit_exact = bool(part_s == exp.size and np.array_equal(got, exp))
+    kv_sample = sum(a.size for a in segs[:sample]) - 10 * sample - 2 * sum(nrec[:sample])
+    cpu = {"value": round(kv_sample / secs / 1e9, 4), "unit": "GB/s", "cores": 1, "kind": "port",
+           "sample": "%d of the %d segments (%d records) through the TezMerger restatement, factor 100, one thread "
+                     "(a TezMerger merge is single-threaded), %.1f s" % (sample, nseg, n_cpu, secs)}
+    line = {"metric": METRIC.replace("(16B key / 64B val)", "(k-way merge, Text keys)"), "value": round(value, 3), "unit": "GB/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "BASELINE config 3: k-way TezMerger of %d sorted IFile segments of %d MiB, Text keys U[4,24] from a "
+                                   "2^24-word space, 8 B values, REPEAT_KEY output" % (nseg, args.c3_segment_mb),
+                       "segments": nseg, "records": records, "input_bytes": in_bytes, "output_bytes": int(part),
+                       "l2": "inputs larger than L2, no flush needed", "timing": "host clock around fully synchronised library calls",
+                       "generation_s": round(t_gen, 1)},
+            "clocks": clk, "e2e": None, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "whole merge step (parse + sort + emit)", "achieved": round(algo / (ms_step * 1e-3) / 1e9, 1),
+                         "peak": peak, "unit": "GB/s", "frac": round(algo / (ms_step * 1e-3) / 1e9 / peak, 4), "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo),
+                         "note": "algorithmic bytes = segment bytes read + merged bytes written (SURVEY 8d)"},
+            "phases_ms": {k: round(v, 3) for k, v in st.items() if k.startswith("ms_")},
+            "parity": {"crc32_of_full_output_matches_zlib": bool(crc_ok), "bit_exact_vs_oracle_on_sample": bit_exact,
+                       "sample_segments": sample},
+            "cpu_baseline": cpu}
+    print(json.dumps(line))
+    assert crc_ok and bit_exact, "config 3 output differs from the checker"
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -374,6 +466,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-g1-pipeline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, help="2 (default, the driver's line) or 3 (k-way merge, one GPU)")
+    ap.add_argument("--c3-segments", type=int, default=256)
+    ap.add_argument("--c3-segment-mb", type=int, default=64)
+    ap.add_argument("--c3-cpu-segments", type=int, default=16)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.records is None:
@@ -382,6 +478,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return reference_arm(args)
+    if args.config == 3:
+        return config3(args)
     if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         return single_gpu(args)
     from tez_b200 import multigpu_bench

@@ -741,6 +741,21 @@ static int seg_len_cmp(const void *a, const void *b) {
   return x->length < y->length ? -1 : 1;
 }
 
+/* when set, tzo_merge() only produces the writeFile output and the record count (no per-record stream): large merges */
+static __thread int g_merge_ifile_only = 0;
+
+int tzo_merge_ifile(const tzo_segment *segs, int nseg, int cmp_kind, int factor, int sort_segments, int check_for_same_keys,
+                    int writer_rle, tzo_merge_result *res, double *seconds) {
+  struct timespec t0, t1;
+  g_merge_ifile_only = 1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  int rc = tzo_merge(segs, nseg, cmp_kind, factor, sort_segments, check_for_same_keys, writer_rle, res);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  g_merge_ifile_only = 0;
+  if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  return rc;
+}
+
 int tzo_merge(const tzo_segment *segs, int nseg, int cmp_kind, int factor, int sort_segments, int check_for_same_keys,
               int writer_rle, tzo_merge_result *res) {
   memset(res, 0, sizeof(*res));
@@ -845,18 +860,20 @@ int tzo_merge(const tzo_segment *segs, int nseg, int cmp_kind, int factor, int s
     int nlive = 0;
     for (int t = 1; t <= it.q.size; t++) live[nlive++] = it.q.heap[t];
     while (mi_next(&it)) {
-      if (res->n == cap) {
+      if (!g_merge_ifile_only && res->n == cap) {
         cap *= 2;
         res->key_len = (uint32_t *)realloc(res->key_len, cap * 4);
         res->val_len = (uint32_t *)realloc(res->val_len, cap * 4);
         res->same_key = (uint8_t *)realloc(res->same_key, cap);
       }
       int same = mi_is_same(&it);
-      res->key_len[res->n] = (uint32_t)it.klen;
-      res->val_len[res->n] = (uint32_t)it.vlen;
-      res->same_key[res->n] = (uint8_t)same;
-      tzo_buf_put(&res->keys, it.key, (size_t)it.klen);
-      tzo_buf_put(&res->vals, it.val, (size_t)it.vlen);
+      if (!g_merge_ifile_only) {
+        res->key_len[res->n] = (uint32_t)it.klen;
+        res->val_len[res->n] = (uint32_t)it.vlen;
+        res->same_key[res->n] = (uint8_t)same;
+        tzo_buf_put(&res->keys, it.key, (size_t)it.klen);
+        tzo_buf_put(&res->vals, it.val, (size_t)it.vlen);
+      }
       res->n++;
       /* TezMerger.writeFile :215-245 */
       if (same) tzo_writer_append(&fw, NULL, 0, it.val, it.vlen);
@@ -895,6 +912,85 @@ void tzo_gen_c2(uint8_t *dst, uint64_t first_index, uint64_t n, uint64_t seed) {
     uint8_t *d = dst + r * 80;
     for (int w = 0; w < 10; w++) put_be64(d + 8 * w, tzo_splitmix64((seed << 56) ^ (i * 16 + (uint64_t)w)));
   }
+}
+
+/* sorted IFile segments of (Text word, 8-byte value = f(word)); words from a 2^24-id space, length
+ * U[4,24] lower-case letters, both functions of the id alone; uncompressed, no run-length encoding in the inputs */
+int tzo_c3_word(uint32_t id, uint8_t *out /* >= 24 bytes */) {
+  uint64_t h = tzo_splitmix64(0xC3C3C3C3ull ^ ((uint64_t)id << 20));
+  int len = 4 + (int)(h % 21);
+  uint64_t r = 0;
+  for (int i = 0; i < len; i++) {
+    if ((i & 7) == 0) r = tzo_splitmix64(((uint64_t)id << 8) | (uint64_t)(i >> 3) | 0x5000000000ull);
+    out[i] = (uint8_t)('a' + (r & 0xFF) % 26);
+    r >>= 8;
+  }
+  return len;
+}
+
+typedef struct { uint8_t len; uint8_t w[24]; uint32_t id; } c3_rec;
+static int c3_cmp(const void *a, const void *b) {
+  const c3_rec *x = (const c3_rec *)a, *y = (const c3_rec *)b;
+  int n = x->len < y->len ? x->len : y->len;
+  int c = memcmp(x->w, y->w, (size_t)n);
+  if (c) return c;
+  return (int)x->len - (int)y->len;
+}
+
+void tzo_gen_c3_segment(uint64_t seed, uint32_t seg_index, uint64_t target_bytes, int id_bits, tzo_buf *out, uint64_t *nrecords) {
+  const uint32_t id_mask = id_bits >= 32 ? 0xFFFFFFFFu : ((1u << id_bits) - 1u);
+  uint64_t cap = target_bytes / 15 + 16, n = 0, bytes = 10;
+  c3_rec *recs = (c3_rec *)malloc(cap * sizeof(c3_rec));
+  for (uint64_t i = 0; bytes < target_bytes && n < cap; i++) {
+    uint32_t id = (uint32_t)(tzo_splitmix64((seed << 56) ^ ((uint64_t)seg_index << 36) ^ i)) & id_mask;
+    recs[n].id = id;
+    recs[n].len = (uint8_t)tzo_c3_word(id, recs[n].w);
+    bytes += 2u + 1u + recs[n].len + 8u;
+    n++;
+  }
+  qsort(recs, n, sizeof(c3_rec), c3_cmp);
+  /* every word at most once per segment (what a map-side combiner leaves): with duplicates INSIDE an unencoded segment
+   * whose key also occurs in other segments, the reference's REPEAT_KEY placement depends on its heap's tie order
+   * (parity unpinned) and the merged bytes would not be defined by the input alone */
+  uint64_t m = 0;
+  for (uint64_t i = 0; i < n; i++)
+    if (m == 0 || c3_cmp(&recs[m - 1], &recs[i]) != 0) recs[m++] = recs[i];
+  n = m;
+  tzo_ifile_writer w;
+  tzo_writer_open(&w, out, 0);
+  uint8_t key[32], val[8];
+  for (uint64_t i = 0; i < n; i++) {
+    key[0] = recs[i].len;                       /* Text: vint(byte length) + UTF-8 */
+    memcpy(key + 1, recs[i].w, recs[i].len);
+    put_be64(val, tzo_splitmix64(0xABCDull ^ ((uint64_t)recs[i].id << 16)));
+    tzo_writer_append(&w, key, 1 + recs[i].len, val, 8);
+  }
+  tzo_writer_close(&w);
+  free(recs);
+  if (nrecords) *nrecords = n;
+}
+
+typedef struct { uint64_t seed, target; uint32_t first, count, stride; int id_bits; tzo_buf *outs; uint64_t *nrec; } c3_job;
+static void *c3_worker(void *arg) {
+  c3_job *j = (c3_job *)arg;
+  for (uint32_t s = j->first; s < j->count; s += j->stride) {
+    tzo_buf_init(&j->outs[s]);
+    tzo_gen_c3_segment(j->seed, s, j->target, j->id_bits, &j->outs[s], &j->nrec[s]);
+  }
+  return NULL;
+}
+void tzo_gen_c3_segments(uint64_t seed, uint32_t nseg, uint64_t target_bytes, int id_bits, int threads, tzo_buf *outs, uint64_t *nrec) {
+  if (threads < 1) threads = 1;
+  if ((uint32_t)threads > nseg) threads = (int)nseg;
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+  c3_job *jobs = (c3_job *)calloc((size_t)threads, sizeof(c3_job));
+  for (int t = 0; t < threads; t++) {
+    jobs[t].seed = seed; jobs[t].target = target_bytes; jobs[t].first = (uint32_t)t; jobs[t].count = nseg;
+    jobs[t].stride = (uint32_t)threads; jobs[t].id_bits = id_bits; jobs[t].outs = outs; jobs[t].nrec = nrec;
+    pthread_create(&th[t], NULL, c3_worker, &jobs[t]);
+  }
+  for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+  free(th); free(jobs);
 }
 
 /* ------------------------------------------------------------------ CPU baseline driver */

@@ -182,6 +182,15 @@ uint64_t tzo_splitmix64(uint64_t x);
 /* C2 generator: record i = 16B key (two BE splitmix64 words) + 64B value (8 BE words) */
 void tzo_gen_c2(uint8_t *dst, uint64_t first_index, uint64_t n, uint64_t seed);
 
+/* same, producing only the writeFile output + record count (res->n) -- no per-record stream; wall time in *seconds */
+int tzo_merge_ifile(const tzo_segment *segs, int nseg, int cmp_kind, int factor, int sort_segments,
+                    int check_for_same_keys, int writer_rle, tzo_merge_result *res, double *seconds);
+
+/* C3 generator: sorted IFile segments of (Text word from a 2^24-id space, 8-byte value = f(word)) */
+int tzo_c3_word(uint32_t id, uint8_t *out);
+void tzo_gen_c3_segment(uint64_t seed, uint32_t seg_index, uint64_t target_bytes, int id_bits, tzo_buf *out, uint64_t *nrecords);
+void tzo_gen_c3_segments(uint64_t seed, uint32_t nseg, uint64_t target_bytes, int id_bits, int threads, tzo_buf *outs, uint64_t *nrec);
+
 /* multi-threaded CPU baseline: T independent PipelinedSorter tasks over slices (one task per thread, as Tez runs one map task per core) */
 double tzo_bench_pipelined_fixed(const tzo_sorter_conf *conf, const uint8_t *kv, uint32_t klen, uint32_t vlen,
                                  uint64_t n, int tasks, uint64_t *out_bytes);

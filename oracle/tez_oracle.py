@@ -312,3 +312,45 @@ def bench_pipelined_fixed(conf, kv, klen, vlen, tasks):
     ob = C.c_uint64()
     secs = lib().tzo_bench_pipelined_fixed(C.byref(conf), kv.ctypes.data, klen, vlen, n, tasks, C.byref(ob))
     return secs, ob.value
+
+
+def gen_c3_segments(nseg, seg_bytes, seed=3, threads=8, id_bits=24):
+    """SURVEY 8(d) C3 generator: nseg sorted IFile segments of about seg_bytes each (Text words from a 2^24-id space,
+    8-byte value = f(word)).  Returns (list of uint8 arrays, list of record counts)."""
+    L = lib()
+    L.tzo_gen_c3_segments.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.POINTER(Buf), C.POINTER(C.c_uint64)]
+    L.tzo_gen_c3_segments.restype = None
+    bufs = (Buf * nseg)()
+    nrec = (C.c_uint64 * nseg)()
+    L.tzo_gen_c3_segments(seed, nseg, seg_bytes, id_bits, threads, bufs, nrec)
+    out = []
+    for b in bufs:
+        a = np.ctypeslib.as_array(b.data, shape=(b.len,)).copy()
+        out.append(a)
+        L.tzo_buf_free(C.byref(b))
+    return out, [int(x) for x in nrec]
+
+
+def merge_ifile(segments, cmp_kind, factor=100, sort_segments=False, check_for_same_keys=True, writer_rle=False):
+    """TezMerger.merge + writeFile for LARGE inputs: returns (ifile bytes as a uint8 array, records, seconds); no
+    per-record Python objects."""
+    L = lib()
+    L.tzo_merge_ifile.argtypes = [C.POINTER(Segment), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(MergeResult), C.POINTER(C.c_double)]
+    L.tzo_merge_ifile.restype = C.c_int
+    arr = (Segment * max(1, len(segments)))()
+    keep = []
+    for i, s in enumerate(segments):
+        a = np.ascontiguousarray(np.frombuffer(s, dtype=np.uint8) if isinstance(s, (bytes, bytearray)) else s)
+        keep.append(a)
+        arr[i].data, arr[i].len, arr[i].has_header = a.ctypes.data, a.size, 1
+    res = MergeResult()
+    secs = C.c_double()
+    rc = L.tzo_merge_ifile(arr, len(segments), cmp_kind, factor, 1 if sort_segments else 0, 1 if check_for_same_keys else 0,
+                           1 if writer_rle else 0, C.byref(res), C.byref(secs))
+    if rc != 0:
+        raise IOError("tzo_merge rc=%d" % rc)
+    out = np.ctypeslib.as_array(res.ifile.data, shape=(res.ifile.len,)).copy()
+    n = int(res.n)
+    L.tzo_merge_result_free(C.byref(res))
+    return out, n, secs.value

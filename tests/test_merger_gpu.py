@@ -242,3 +242,24 @@ def test_write_ifile_on_a_multi_partition_merger_is_rejected():
     with T.GpuMerger(segs, comparator=T.CMP_BYTES, partitions=[0, 1], num_partitions=2) as m:
         with pytest.raises(IOError, match="num_partitions"):
             m.write_ifile()
+
+
+@pytest.mark.parametrize("nseg,seg_kb,id_bits", [(16, 512, 14), (16, 8192, 22), (64, 256, 12)])
+def test_config3_shape_text_merge_bit_exact(nseg, seg_kb, id_bits):
+    """BASELINE config 3 shape: k-way merge of sorted IFile segments with Text keys of length U[4,24] drawn from a small
+    word space (so every word occurs in many segments: large groups of EQUAL keys, REPEAT_KEY output).  Exercises the
+    parallel window parser, the alphabet-compressed sort word and the equal-group shortcut; the merged IFile must equal
+    the oracle's TezMerger.writeFile byte for byte."""
+    segs, nrec = O.gen_c3_segments(nseg, seg_kb << 10, seed=3, threads=8, id_bits=id_bits)
+    exp, n, _ = O.merge_ifile(segs, O.CMP_TEXT, factor=100)
+    with T.GpuMerger([s.tobytes() for s in segs], comparator=T.CMP_TEXT) as m:
+        assert m.counts()[0] == n == sum(nrec)
+        seg, raw, part, st = m.write_ifile()
+    assert part == exp.size
+    assert np.array_equal(np.frombuffer(seg, dtype=np.uint8), exp)
+    # and without the cross-segment check (PipelinedSorter's final merge when the last spill saw few duplicates)
+    exp2, _, _ = O.merge_ifile(segs, O.CMP_TEXT, factor=100, check_for_same_keys=False)
+    with T.GpuMerger([s.tobytes() for s in segs], comparator=T.CMP_TEXT) as m:
+        m.set_check_for_same_keys(False)
+        seg2, _, part2, _ = m.write_ifile()
+    assert np.array_equal(np.frombuffer(seg2, dtype=np.uint8), exp2)

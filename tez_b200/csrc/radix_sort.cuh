@@ -2,6 +2,10 @@
 // 8-bit digit, chained-scan with decoupled look-back across tiles, warp-match ranking, shared-memory reorder so the
 // scatter leaves the SM as contiguous per-digit runs).
 //
+// Tried in round 2 and reverted: a second instantiation of the tile body without the per-item validity predicates
+// (every tile but the last is full) -- 27 % fewer SASS instructions in that path, but the pass got SLOWER on the B200
+// (4 passes 2.30 -> 2.44 ms at 1e8 pairs; twice the code for the instruction cache of a kernel that is issue-bound).
+//
 // Used by the sorter for the (partition|key-prefix, record-index) pairs of the hot path -- the device counterpart of
 // PipelinedSorter's per-span QuickSort + SpanMerger (SORT/PipelinedSorter.java:965-1023,1116-1503) -- and by the
 // tie-refinement / merge stages.  Integer work only; HBM-bound.
@@ -89,18 +93,17 @@ struct OnesweepCfg {
                                  2 * RADIX * 4 + 64 + (TEZGPU_RANK_MODE == 2 ? (size_t)NWARPS * RADIX * 4 : 0);
 };
 
-// FULL: the tile holds exactly TILE keys (every tile but the last): no per-item validity predicates / divergence
-// regions in the ranking, reorder and write-out loops (the pass is issue-bound: ~95 SASS instructions per key).
-template <typename KeyT, int THREADS, int IPT, bool VALS_IOTA, bool FULL>
-__device__ __forceinline__ void onesweep_tile(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
-                                              const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out, uint32_t n,
-                                              int shift, const uint32_t *__restrict__ hist_base, uint32_t *tile_state,
-                                              uint32_t *tile_counter, uint8_t *smem_raw) {
+template <typename KeyT, int THREADS, int IPT, bool VALS_IOTA>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+    k_onesweep_pass(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, const uint32_t *__restrict__ vals_in,
+                    uint32_t *__restrict__ vals_out, uint32_t n, int shift, const uint32_t *__restrict__ hist_base,
+                    uint32_t *tile_state, uint32_t *tile_counter) {
   using Cfg = OnesweepCfg<KeyT, THREADS, IPT>;
   constexpr int NWARPS = Cfg::NWARPS;
   constexpr int TILE = Cfg::TILE;
   static_assert(THREADS >= RADIX, "one thread per digit for the look-back");
 
+  extern __shared__ __align__(16) uint8_t smem_raw[];
   KeyT *s_keys = reinterpret_cast<KeyT *>(smem_raw);
   uint32_t *s_vals = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TILE * sizeof(KeyT));
   uint32_t *s_wcnt = s_vals + TILE;           // [NWARPS][RADIX]
@@ -112,11 +115,24 @@ __device__ __forceinline__ void onesweep_tile(const KeyT *__restrict__ keys_in, 
 #endif
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // Tile id = block index: blocks of a 1-D grid are dispatched in index order, which is what the look-back's forward
+  // progress needs (same assumption as CUB's decoupled look-back scan).  A global ticket counter costs one same-address
+  // atomic per tile -- measured ~20 ns each, i.e. 0.25 ms of a 0.58 ms pass at 12 K tiles.
+#ifdef TEZGPU_TICKET_ATOMIC
+  if (tid == 0) s_misc[0] = atomicAdd(tile_counter, 1u);
+#else
+  if (tid == 0) s_misc[0] = blockIdx.x;
+#endif
+  for (int i = tid; i < NWARPS * RADIX; i += THREADS) s_wcnt[i] = 0;
+#if TEZGPU_RANK_MODE == 2
+  for (int i = tid; i < NWARPS * RADIX; i += THREADS) s_wmask[i] = 0;
+#endif
+  __syncthreads();
   const uint32_t tile = s_misc[0];
   const uint32_t tile_base = tile * (uint32_t)TILE;
-  const uint32_t tile_n = FULL ? (uint32_t)TILE : min((uint32_t)TILE, n - tile_base);
+  const uint32_t tile_n = min((uint32_t)TILE, n - tile_base);
   const uint32_t warp_base = (uint32_t)warp * 32u * IPT;
-  (void)tile_counter;
 
   // ---- load keys (warp-striped => coalesced) and rank them inside the warp
   KeyT key[IPT];
@@ -124,7 +140,7 @@ __device__ __forceinline__ void onesweep_tile(const KeyT *__restrict__ keys_in, 
 #pragma unroll
   for (int j = 0; j < IPT; j++) {
     uint32_t li = warp_base + j * 32 + lane;
-    key[j] = (FULL || li < tile_n) ? keys_in[tile_base + li] : (KeyT)0;
+    key[j] = (li < tile_n) ? keys_in[tile_base + li] : (KeyT)0;
   }
   uint32_t *wc = s_wcnt + warp * RADIX;
   const uint32_t lt = lanemask_lt();
@@ -133,7 +149,7 @@ __device__ __forceinline__ void onesweep_tile(const KeyT *__restrict__ keys_in, 
 #pragma unroll
   for (int j = 0; j < IPT; j++) {
     uint32_t li = warp_base + j * 32 + lane;
-    const bool valid = FULL || li < tile_n;
+    bool valid = li < tile_n;
     uint32_t d = radix_digit(key[j], shift);
     uint32_t peers;
 #if TEZGPU_RANK_MODE == 0
@@ -201,7 +217,7 @@ __device__ __forceinline__ void onesweep_tile(const KeyT *__restrict__ keys_in, 
 #pragma unroll
   for (int j = 0; j < IPT; j++) {
     uint32_t li = warp_base + j * 32 + lane;
-    if (FULL || li < tile_n) {
+    if (li < tile_n) {
       uint32_t d = radix_digit(key[j], shift);
       uint32_t slot = s_dstart[d] + wc[d] + rnk[j];
       s_keys[slot] = key[j];
@@ -248,47 +264,13 @@ __device__ __forceinline__ void onesweep_tile(const KeyT *__restrict__ keys_in, 
 #pragma unroll
   for (int k = 0; k < IPT; k++) {
     uint32_t slot = (uint32_t)tid + k * THREADS;
-    if (FULL || slot < tile_n) {
+    if (slot < tile_n) {
       KeyT kk = s_keys[slot];
       uint32_t dest = s_goff[radix_digit(kk, shift)] + slot;
       keys_out[dest] = kk;
       vals_out[dest] = s_vals[slot];
     }
   }
-}
-
-template <typename KeyT, int THREADS, int IPT, bool VALS_IOTA>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
-    k_onesweep_pass(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, const uint32_t *__restrict__ vals_in,
-                    uint32_t *__restrict__ vals_out, uint32_t n, int shift, const uint32_t *__restrict__ hist_base,
-                    uint32_t *tile_state, uint32_t *tile_counter) {
-  using Cfg = OnesweepCfg<KeyT, THREADS, IPT>;
-  constexpr int NWARPS = Cfg::NWARPS;
-  constexpr int TILE = Cfg::TILE;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  uint32_t *s_vals = reinterpret_cast<uint32_t *>(smem_raw + (size_t)TILE * sizeof(KeyT));
-  uint32_t *s_wcnt = s_vals + TILE;
-  uint32_t *s_misc = s_wcnt + NWARPS * RADIX + 2 * RADIX;
-  const int tid = threadIdx.x;
-  // Tile id = block index: blocks of a 1-D grid are dispatched in index order, which is what the look-back's forward
-  // progress needs (same assumption as CUB's decoupled look-back scan).  A global ticket counter costs one same-address
-  // atomic per tile -- measured ~20 ns each, i.e. 0.25 ms of a 0.58 ms pass at 12 K tiles.
-#ifdef TEZGPU_TICKET_ATOMIC
-  if (tid == 0) s_misc[0] = atomicAdd(tile_counter, 1u);
-#else
-  if (tid == 0) s_misc[0] = blockIdx.x;
-#endif
-  for (int i = tid; i < NWARPS * RADIX; i += THREADS) s_wcnt[i] = 0;
-#if TEZGPU_RANK_MODE == 2
-  uint32_t *s_wmask = s_misc + 16;
-  for (int i = tid; i < NWARPS * RADIX; i += THREADS) s_wmask[i] = 0;
-#endif
-  __syncthreads();
-  const uint32_t tile = s_misc[0];
-  if ((uint64_t)(tile + 1) * TILE <= n)
-    onesweep_tile<KeyT, THREADS, IPT, VALS_IOTA, true>(keys_in, keys_out, vals_in, vals_out, n, shift, hist_base, tile_state, tile_counter, smem_raw);
-  else
-    onesweep_tile<KeyT, THREADS, IPT, VALS_IOTA, false>(keys_in, keys_out, vals_in, vals_out, n, shift, hist_base, tile_state, tile_counter, smem_raw);
 }
 
 // ------------------------------------------------------------------------------------------------ host driver

@@ -53,7 +53,7 @@ class SortPipeline {
 
   // workspace (grow-only, reused across flushes)
   DeviceBuffer keysA, keysB, valsA, valsB, same, blk, small, tile_state, sizes, rec_off;
-  DeviceBuffer t_pos[2], t_gid[2], t_lidx[2], t_key64[2], t_val[2], t_state;
+  DeviceBuffer t_pos[2], t_gid[2], t_lidx[2], t_key64[2], t_val[2], t_state, t_ghead, t_gneq, sym_sets, sym_tab;
   DeviceBuffer seg_start, tile_start, part_start, d_index, seg_crc, tile_desc, tile_crc, tie_state;
   PinnedBuffer h_small;
 
@@ -228,6 +228,44 @@ class SortPipeline {
     uint32_t *K = keysA.as<uint32_t>();
     uint32_t *order = valsA.as<uint32_t>();
 
+    uint32_t sym_npos = 0;
+    if (n && !rec.fixed && !(getenv("TEZGPU_NO_SYM") && atoi(getenv("TEZGPU_NO_SYM")))) {
+      // ---------------- alphabet-compressed sort word (SymTable, sorter_kernels.cuh): which byte values occur at the
+      // first content positions -> per-position ranks, packed while they fit the (32 - pbits)-bit key field
+      sym_sets.ensure(SYM_MAX_POS * 8 * 4);
+      sym_tab.ensure(sizeof(SymTable));
+      TG_CUDA(cudaMemsetAsync(sym_sets.p, 0, SYM_MAX_POS * 8 * 4, stream));
+      k_symbols<<<(int)std::min<uint64_t>(div_up(n, 256), (uint64_t)num_sms * 8), 256, 0, stream>>>(rec, sym_sets.as<uint32_t>());
+      launches++;
+      uint32_t hs[SYM_MAX_POS * 8];
+      TG_CUDA(cudaMemcpyAsync(hs, sym_sets.p, sizeof(hs), cudaMemcpyDeviceToHost, stream));
+      TG_CUDA(cudaStreamSynchronize(stream));
+      SymTable *t = new SymTable();
+      memset(t, 0, sizeof(*t));
+      const uint32_t avail = 32u - (uint32_t)pbits;
+      uint32_t used = 0, np = 0;
+      for (; np < (uint32_t)SYM_MAX_POS; np++) {
+        uint32_t cnt = 0;
+        for (int w = 0; w < 8; w++) cnt += (uint32_t)__builtin_popcount(hs[np * 8 + w]);
+        if (cnt == 0) break;                       // no key is this long
+        uint32_t bits = 0;
+        while ((1u << bits) < cnt + 1) bits++;     // ranks 1..cnt, 0 = the key ended
+        if (used + bits > avail) break;
+        used += bits;
+        t->shift[np] = (uint8_t)(avail - used);
+        uint32_t rk = 0;
+        for (uint32_t b = 0; b < 256; b++)
+          if ((hs[np * 8 + (b >> 5)] >> (b & 31u)) & 1u) t->rank[np][b] = (uint8_t)(++rk);
+      }
+      t->npos = np;
+      if (np > avail / 8) {                        // packs more positions than the raw bytes would
+        TG_CUDA(cudaMemcpyAsync(sym_tab.p, t, sizeof(SymTable), cudaMemcpyHostToDevice, stream));
+        TG_CUDA(cudaStreamSynchronize(stream));
+        rec.sym = sym_tab.as<SymTable>();
+        sym_npos = np;
+      }
+      delete t;
+    }
     if (n) {
       // ---------------- stage
       TG_CUDA(cudaMemsetAsync(same.p, 0, n, stream));
@@ -259,7 +297,8 @@ class SortPipeline {
       // One streaming kernel finds the groups and orders the (common) small ones in place; the partition bounds and
       // -- for fixed-width records -- the segment layout are computed speculatively so that the whole common path needs a
       // single host round trip (tie count, large groups, duplicates, error flag, layout totals).
-      const uint32_t depth0 = (uint32_t)((32 - pbits) / 8);
+      // normalised content bytes the sort word fully covers (equal words <=> equal on these bytes)
+      const uint32_t depth0 = rec.sym ? sym_npos : (uint32_t)((32 - pbits) / 8);
       int per_sm_tf = 0;
       TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tf, k_tie_fix, TIEFIX_THREADS, 0));
       k_tie_fix<<<(uint32_t)std::min<uint64_t>(div_up(n, TIEFIX_TILE), (uint64_t)num_sms * std::max(per_sm_tf, 1)), TIEFIX_THREADS, 0, stream>>>(
@@ -304,11 +343,39 @@ class SortPipeline {
         k_tie_compact<<<nblk, SCAN_THREADS, 0, stream>>>(K, order, n, blk.as<uint64_t>(), t_pos[0].as<uint32_t>(),
                                                          t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>());
         launches += 3;
-        // positions already fixed in place keep their (correct) same[] flags: the rounds below recompute every tied
-        // record anyway, so restart the duplicate count
-        TG_CUDA(cudaMemsetAsync(d_dups(), 0, 8, stream));
-        uint32_t depth = depth0;
+        // ---- groups larger than TIE_SMALL_MAX whose members all carry the same key need no ordering (the radix sort
+        // is stable): settle them here; only groups with really different keys go through the refinement rounds.
+        // Small groups keep the order, flags and duplicate count k_tie_fix gave them.
+        const uint32_t ngroups = (uint32_t)(hs[0] >> 32);
         int cur = 0;
+        {
+          t_ghead.ensure(((size_t)ngroups + 2) * 4);
+          t_gneq.ensure((size_t)ngroups + 1);
+          TG_CUDA(cudaMemsetAsync(t_gneq.p, 0, (size_t)ngroups + 1, stream));
+          const uint32_t mgrid = (uint32_t)div_up(m, 256), mblk0 = (uint32_t)div_up(m, SCAN_TILE);
+          k_group_heads<<<mgrid, 256, 0, stream>>>(t_gid[0].as<uint32_t>(), m, t_ghead.as<uint32_t>());
+          k_group_equal<<<mgrid, 256, 0, stream>>>(rec, t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>(), t_ghead.as<uint32_t>(), m, depth0,
+                                                 TIE_SMALL_MAX, t_gneq.as<uint8_t>());
+          blk.ensure(((size_t)std::max(mblk0, nblk) + 2) * 8);
+          k_group_mark<<<mblk0, SCAN_THREADS, 0, stream>>>(t_pos[0].as<uint32_t>(), t_gid[0].as<uint32_t>(), t_ghead.as<uint32_t>(),
+                                                          t_gneq.as<uint8_t>(), m, TIE_SMALL_MAX, same.as<uint8_t>(), d_dups(), blk.as<uint64_t>());
+          k_scan_block_sums<<<1, 1024, 0, stream>>>(blk.as<uint64_t>(), mblk0);
+          launches += 4;
+          TG_CUDA(cudaGetLastError());
+          TG_CUDA(cudaMemcpyAsync(&hs[0], blk.as<uint64_t>() + mblk0, 8, cudaMemcpyDeviceToHost, stream));
+          TG_CUDA(cudaStreamSynchronize(stream));
+          const uint32_t m2 = (uint32_t)hs[0];
+          if (m2) {
+            k_group_compact<<<mblk0, SCAN_THREADS, 0, stream>>>(t_pos[0].as<uint32_t>(), t_gid[0].as<uint32_t>(), t_lidx[0].as<uint32_t>(),
+                                                               t_ghead.as<uint32_t>(), t_gneq.as<uint8_t>(), m, TIE_SMALL_MAX, blk.as<uint64_t>(),
+                                                               t_pos[1].as<uint32_t>(), t_gid[1].as<uint32_t>(), t_lidx[1].as<uint32_t>());
+            launches++;
+            TG_CUDA(cudaGetLastError());
+            cur = 1;
+          }
+          m = m2;
+        }
+        uint32_t depth = depth0;
         while (m) {
           t_key64[0].ensure((size_t)m * 8); t_key64[1].ensure((size_t)m * 8); t_val[0].ensure((size_t)m * 4);
           const uint32_t mblk = (uint32_t)div_up(m, SCAN_TILE);

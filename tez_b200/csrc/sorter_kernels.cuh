@@ -51,6 +51,20 @@ __device__ __forceinline__ uint64_t run_record_off_p(const RunTable &t, uint32_t
   return __ldg(t.seg_off + seg) + (uint64_t)(i - __ldg(t.rec_base + seg)) * t.rec_size;
 }
 
+// Alphabet-compressed sort word for variable-length keys.  The 32-bit sort word normally holds the first
+// (32 - pbits) / 8 normalised content bytes; keys over a small alphabet (text: 26 letters) waste most of those bits,
+// everything ties on the prefix and the whole order is left to the key-suffix refinement.  Instead, a pass over the keys
+// records WHICH byte values occur at each of the first SYM_MAX_POS content positions; position q then needs only
+// ceil(log2(#values + 1)) bits (rank 0 = "key ended before q", so a proper prefix still sorts first), and as many
+// positions as fit are packed, most significant first.  Order-preserving by construction (ranks follow byte order per
+// position), exact for any input; lower-case words get 6 characters into 30 bits instead of 3-4.
+constexpr int SYM_MAX_POS = 16;
+struct SymTable {
+  uint8_t rank[SYM_MAX_POS][256];  // 1 + number of occurring byte values below b (0 for values that never occur)
+  uint8_t shift[SYM_MAX_POS];      // left shift of position q's rank inside the (32 - pbits)-bit field
+  uint32_t npos;                   // positions packed; equal sort words <=> equal first npos content bytes (or both ended)
+};
+
 // Collected records as they sit in HBM (the analogue of PipelinedSorter's kvbuffer + kvmeta, :957-959)
 struct Records {
   const uint8_t *kv;        // serialized bytes, key immediately followed by value
@@ -70,6 +84,7 @@ struct Records {
   int pbits;  // bits of the sort word that hold the partition
   int use_runs;   // fixed mode: records are addressed through `runs` instead of index * stride / key_off
   RunTable runs;
+  const SymTable *sym;  // optional alphabet-compressed sort word (variable-length keys)
 };
 
 __device__ __forceinline__ void record_lookup(const Records &r, uint32_t i, uint64_t &koff, uint32_t &klen,
@@ -153,8 +168,15 @@ __global__ void __launch_bounds__(256) k_stage(Records r, uint32_t *__restrict__
       const uint8_t *content = key + skip;
       uint32_t clen = klen - skip;
       prefix = 0;
+      if (r.sym) {   // packed ranks: already a (32 - pbits)-bit value, shifted up so that the common `>> pbits` below fits
+        const SymTable *__restrict__ st = r.sym;
+        const uint32_t np = st->npos;
+        for (uint32_t q = 0; q < np && q < clen; q++) prefix |= (uint32_t)st->rank[q][norm_byte(r.cmp, content, q)] << st->shift[q];
+        prefix <<= r.pbits;
+      } else {
 #pragma unroll
-      for (uint32_t b = 0; b < 4; b++) prefix = (prefix << 8) | (b < clen ? norm_byte(r.cmp, content, b) : 0u);
+        for (uint32_t b = 0; b < 4; b++) prefix = (prefix << 8) | (b < clen ? norm_byte(r.cmp, content, b) : 0u);
+      }
       p = r.hash_partition ? (int32_t)((uint32_t)(key_hash_dev(r.cmp, key, klen) & 0x7fffffff) % (uint32_t)r.num_partitions)
                            : ((r.fixed && r.use_runs) ? run_part : (r.partition ? r.partition[i] : 0));
     }
@@ -172,6 +194,31 @@ __global__ void __launch_bounds__(256) k_stage(Records r, uint32_t *__restrict__
     uint32_t c = s_hist[i];
     if (c) atomicAdd(&hist[i], c);
   }
+}
+
+// which byte values occur at each of the first SYM_MAX_POS normalised content positions: sets[q][b >> 5] bit (b & 31)
+__global__ void __launch_bounds__(256) k_symbols(Records r, uint32_t *__restrict__ sets /*[SYM_MAX_POS][8]*/) {
+  __shared__ uint32_t s_set[SYM_MAX_POS * 8];
+  for (int i = threadIdx.x; i < SYM_MAX_POS * 8; i += blockDim.x) s_set[i] = 0;
+  __syncthreads();
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < r.n; i += stride) {
+    uint64_t koff;
+    uint32_t klen, vlen;
+    record_lookup(r, i, koff, klen, vlen);
+    const uint8_t *key = r.kv + koff;
+    const uint32_t skip = key_content_skip(r.cmp, key, klen);
+    const uint8_t *content = key + skip;
+    const uint32_t clen = klen - skip;
+    for (uint32_t q = 0; q < (uint32_t)SYM_MAX_POS && q < clen; q++) {
+      const uint32_t b = norm_byte(r.cmp, content, q);
+      const uint32_t bit = 1u << (b & 31u);
+      if (!(s_set[q * 8 + (b >> 5)] & bit)) atomicOr(&s_set[q * 8 + (b >> 5)], bit);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SYM_MAX_POS * 8; i += blockDim.x)
+    if (s_set[i]) atomicOr(&sets[i], s_set[i]);
 }
 
 // ------------------------------------------------------------------------------------------------ tie detection
@@ -267,6 +314,96 @@ __global__ void __launch_bounds__(SCAN_THREADS)
       pos[at] = i;
       gid[at] = heads - 1;
       lidx[at] = order[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ equal-key groups
+// Large tie groups are usually large because the SAME key occurs many times (a reduce-side merge of word counts, a
+// 2^24-word key space spread over 256 runs): such a group needs no ordering at all -- the radix sort is stable, so its
+// members already stand in (run, position) order -- only its same[] flags.  These kernels test every group larger than
+// TIE_SMALL_MAX for "all members equal to the first" and settle those; only groups that really contain different keys
+// go on to the key-suffix refinement rounds.  Input: the compacted tied list (pos, gid, lidx) of k_tie_compact.
+__global__ void __launch_bounds__(256) k_group_heads(const uint32_t *__restrict__ gid, uint32_t m, uint32_t *__restrict__ ghead) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const uint32_t g = gid[j];
+  if (j == 0 || gid[j - 1] != g) ghead[g] = j;
+  if (j + 1 == m) ghead[g + 1] = m;
+}
+
+__device__ __forceinline__ int compare_keys_from(const Records &r, uint32_t ra, uint32_t rb, uint32_t depth);
+
+__global__ void __launch_bounds__(256)
+    k_group_equal(Records r, const uint32_t *__restrict__ gid, const uint32_t *__restrict__ lidx, const uint32_t *__restrict__ ghead,
+                  uint32_t m, uint32_t depth, uint32_t small_max, uint8_t *__restrict__ gneq) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const uint32_t g = gid[j], h = ghead[g];
+  if (ghead[g + 1] - h <= small_max || j == h) return;     // small groups were ordered in place by k_tie_fix
+  if (compare_keys_from(r, lidx[h], lidx[j], depth) != 0) gneq[g] = 1;
+}
+
+// settles the all-equal large groups (flags + duplicate count) and counts what still needs refinement:
+// blk[b] = survivors | heads of surviving groups << 32
+__global__ void __launch_bounds__(SCAN_THREADS)
+    k_group_mark(const uint32_t *__restrict__ pos, const uint32_t *__restrict__ gid, const uint32_t *__restrict__ ghead,
+                 const uint8_t *__restrict__ gneq, uint32_t m, uint32_t small_max, uint8_t *__restrict__ same,
+                 unsigned long long *__restrict__ dup_count, uint64_t *__restrict__ blk) {
+  __shared__ uint64_t s_warp[SCAN_THREADS / 32];
+  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
+  uint64_t sv = 0;
+  uint32_t dups = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; k++) {
+    const uint32_t j = base + k;
+    if (j < m) {
+      const uint32_t g = gid[j], h = ghead[g];
+      if (ghead[g + 1] - h > small_max) {
+        if (gneq[g]) sv += 1ull | ((uint64_t)(j == h) << 32);
+        else if (j != h) { same[pos[j]] = 1; dups++; }
+      }
+    }
+  }
+  uint64_t tot;
+  block_exclusive_scan_u64(sv, s_warp, &tot);
+  if (threadIdx.x == 0) blk[blockIdx.x] = tot;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dups += __shfl_xor_sync(0xffffffffu, dups, o);
+  if ((threadIdx.x & 31) == 0 && dups) atomicAdd(dup_count, (unsigned long long)dups);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+    k_group_compact(const uint32_t *__restrict__ pos, const uint32_t *__restrict__ gid, const uint32_t *__restrict__ lidx,
+                    const uint32_t *__restrict__ ghead, const uint8_t *__restrict__ gneq, uint32_t m, uint32_t small_max,
+                    const uint64_t *__restrict__ blk, uint32_t *__restrict__ pos_out, uint32_t *__restrict__ gid_out,
+                    uint32_t *__restrict__ lidx_out) {
+  __shared__ uint64_t s_warp[SCAN_THREADS / 32];
+  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_IPT;
+  bool keep[SCAN_IPT], head[SCAN_IPT];
+  uint64_t sv = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; k++) {
+    const uint32_t j = base + k;
+    keep[k] = head[k] = false;
+    if (j < m) {
+      const uint32_t g = gid[j], h = ghead[g];
+      keep[k] = (ghead[g + 1] - h > small_max) && gneq[g];
+      head[k] = keep[k] && j == h;
+    }
+    sv += (uint64_t)keep[k] | ((uint64_t)head[k] << 32);
+  }
+  const uint64_t ex = block_exclusive_scan_u64(sv, s_warp, nullptr) + blk[blockIdx.x];
+  uint32_t at = (uint32_t)ex, heads = (uint32_t)(ex >> 32);
+#pragma unroll
+  for (int k = 0; k < SCAN_IPT; k++) {
+    if (keep[k]) {
+      if (head[k]) heads++;
+      const uint32_t j = base + k;
+      pos_out[at] = pos[j];
+      gid_out[at] = heads - 1;
+      lidx_out[at] = lidx[j];
+      at++;
     }
   }
 }
