@@ -245,6 +245,10 @@ uint32_t tezgpu_debug_assemble_emulate(const uint8_t *stage, uint32_t nr, uint32
                                        uint32_t hdr_len, uint32_t lead, int32_t first, int32_t last, uint8_t *image_out,
                                        uint32_t image_cap);
 
+uint32_t tezgpu_debug_runs_assemble_emulate(const uint8_t *staging, uint32_t staging_len, const uint32_t *src, uint32_t nr,
+                                            uint32_t rec_size, uint32_t lead, int32_t first, int32_t last,
+                                            uint8_t *image_out, uint32_t image_cap);
+
 #ifdef __cplusplus
 }
 #endif

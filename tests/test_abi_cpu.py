@@ -76,3 +76,46 @@ def test_tma_emit_chunk_assembly_matches_the_byte_image():
                             assert out[lead:end].tobytes() == bytes(img[lead:]), (stride, hdr, nr, lead, first, last)
                             cases += 1
     assert cases > 3000
+
+
+def test_run_range_emit_chunk_assembly_matches_the_byte_image():
+    """emit_runs.cuh (reduce side, fixed-framing runs in place): the tile's records sit in a few contiguous byte ranges
+    of the input segments, copied into shared memory at arbitrary alignments; every aligned 16-byte chunk of the output
+    is assembled from the one or two records it covers.  Same template code on the host against the concatenation."""
+    import numpy as np
+    L = _lib.load()
+    rng = random.Random(3)
+    cases = 0
+    for rec_size in (17, 18, 33, 82, 83, 100, 4114):
+        for nr in (1, 2, 5, 64, 255, 256):
+            if nr * rec_size > 400000:
+                continue
+            for lead in (0, 1, 6, 11, 15):
+                for first in (0, 1):
+                    for last in (0, 1):
+                        nruns = rng.randint(1, min(8, nr))
+                        assign = [rng.randrange(nruns) for _ in range(nr)]
+                        sizes = [assign.count(g) for g in range(nruns)]
+                        staging, run_off = bytearray(), []
+                        for g in range(nruns):
+                            staging += bytes((16 - len(staging) % 16) % 16) + rng.randbytes(rng.randint(0, 15))
+                            run_off.append(len(staging))
+                            staging += bytes(sizes[g] * rec_size)
+                        recs = [rng.randbytes(rec_size) for _ in range(nr)]
+                        at, src = [0] * nruns, []
+                        for j in range(nr):
+                            o = run_off[assign[j]] + at[assign[j]] * rec_size
+                            at[assign[j]] += 1
+                            staging[o:o + rec_size] = recs[j]
+                            src.append(o)
+                        img = bytearray(lead) + (b"TIF\x00" if first else b"") + b"".join(recs) + (b"\xff\xff" if last else b"")
+                        cap = (len(img) + 31) // 16 * 16
+                        out = np.zeros(cap, dtype=np.uint8)
+                        st = np.frombuffer(bytes(staging), dtype=np.uint8).copy()
+                        sa = np.array(src, dtype=np.uint32)
+                        end = L.tezgpu_debug_runs_assemble_emulate(st.ctypes.data, len(st), sa.ctypes.data, nr, rec_size, lead,
+                                                                   first, last, out.ctypes.data, cap)
+                        assert end == len(img)
+                        assert out[lead:end].tobytes() == bytes(img[lead:]), (rec_size, nr, lead, first, last)
+                        cases += 1
+    assert cases >= 700

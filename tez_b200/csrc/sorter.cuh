@@ -13,6 +13,7 @@
 #endif
 #include "emit_pipe_u.cuh"
 #include "emit_tma.cuh"
+#include "emit_runs.cuh"
 #include "sorter_kernels.cuh"
 
 namespace tezgpu {
@@ -120,6 +121,11 @@ class SortPipeline {
   // (every segment had the plain fixed framing), which together decide whether any record can be written as a repeat
   int merge_check_same = 1;
   bool merge_inputs_plain = false;
+  uint32_t merge_max_runs = 0;   // run-table mode: most runs any output partition has (emit_runs.cuh plans <= 32 per warp)
+  static bool runs_emit_enabled() {
+    static const bool on = !(getenv("TEZGPU_EMIT_RUNS") && atoi(getenv("TEZGPU_EMIT_RUNS")) == 0);
+    return on;
+  }
 
   EmitParams make_emit_params(const Records &rec, const uint32_t *order, int rle, bool merge_mode, uint8_t *d_out) {
     EmitParams e;
@@ -145,7 +151,7 @@ class SortPipeline {
     static const bool on = !(getenv("TEZGPU_EMIT_PIPE_UNALIGNED") && atoi(getenv("TEZGPU_EMIT_PIPE_UNALIGNED")) == 0);
     return on;
   }
-  static void set_fixed_layout(EmitParams &e, const Records &rec) {
+  void set_fixed_layout(EmitParams &e, const Records &rec) {
     int h = 0;
     for (int b = 0; b < vint_size_u32(rec.klen); b++) e.fixed_hdr[h++] = vint_byte_u32(rec.klen, b);
     for (int b = 0; b < vint_size_u32(rec.vlen); b++) e.fixed_hdr[h++] = vint_byte_u32(rec.vlen, b);
@@ -158,7 +164,9 @@ class SortPipeline {
     // within 10 % of the cap, take the one with the most records per executed round (249 for 82-byte records).
     static const int round_fill = getenv("TEZGPU_EMIT_ROUND_FILL") ? atoi(getenv("TEZGPU_EMIT_ROUND_FILL")) : TEZGPU_EMIT_ROUND_FILL_DEFAULT;
     bool fill = round_fill != 0;
-    if (pipe_unaligned_enabled()) {
+    if (rec.use_runs && runs_emit_enabled() && emit_runs_fits(e.recs_per_tile, e.rec_size, merge_max_runs)) {
+      // run-table mode with the range-copy emit (emit_runs.cuh): full 256-record tiles
+    } else if (pipe_unaligned_enabled()) {
       // the pipelined kernel for records at arbitrary offsets (emit_pipe_u.cuh) holds a tile's words in five gather rounds
       const uint32_t stride = rec.klen + rec.vlen;
       const bool fast = stride >= 16 && stride % 16 == 0;
@@ -563,6 +571,18 @@ class SortPipeline {
             uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));
             k_emit_fast4<FE4_UNROLL, 1><<<grid, FE_THREADS, Emit4Smem<1>::TOTAL, stream>>>(fp);
           }
+        } else if (rec.use_runs && runs_emit_enabled() && emit_runs_fits(e.recs_per_tile, e.rec_size, merge_max_runs)) {
+          // reduce side, fixed-framing runs in place: one bulk copy per run and tile (emit_runs.cuh)
+          const size_t smem = EmitRunsLayout::total(e.recs_per_tile, e.rec_size);
+          static size_t attr_smem = 0;
+          if (smem > attr_smem) {
+            TG_CUDA(cudaFuncSetAttribute(k_emit_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem = smem;
+          }
+          TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_runs, ER_THREADS, smem));
+          uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));
+          k_emit_runs<<<grid, ER_THREADS, smem, stream>>>(fp, (uint32_t)EmitRunsLayout::stage_data(e.recs_per_tile, e.rec_size),
+                                                         (uint32_t)EmitRunsLayout::stage_bytes(e.recs_per_tile, e.rec_size));
         } else if (fast_aligned) {
           TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_fast<5, true>, FE_THREADS, 0));
           uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)num_sms * (per_sm > 0 ? per_sm : 1));

@@ -572,6 +572,30 @@ uint32_t tezgpu_debug_assemble_emulate(const uint8_t *stage, uint32_t nr, uint32
   return body_end;
 }
 
+// Host emulation of the run-range emit kernel's chunk assembly (emit_runs.cuh): record j of the tile is the rec_size
+// bytes at staging[src[j]...]; builds the output image chunk by chunk with the kernel's template code.
+uint32_t tezgpu_debug_runs_assemble_emulate(const uint8_t *staging, uint32_t staging_len, const uint32_t *src, uint32_t nr,
+                                            uint32_t rec_size, uint32_t lead, int32_t first, int32_t last, uint8_t *image_out,
+                                            uint32_t image_cap) {
+  std::vector<uint8_t> padded((size_t)staging_len + 64, 0);
+  memcpy(padded.data(), staging, staging_len);
+  HostSmem sm{padded.data()};
+  RunsTileGeom g;
+  g.src = src;
+  g.nr = nr;
+  g.first = first != 0;
+  g.last = last != 0;
+  g.rec0 = lead + (g.first ? 4u : 0u);
+  g.body = nr * rec_size;
+  const uint32_t magic = (uint32_t)((1ull << 32) / rec_size) + 1u;
+  const uint32_t body_end = g.rec0 + g.body + (g.last ? 2u : 0u);
+  for (uint32_t c = lead >> 4; 16u * c < body_end && 16u * c + 16u <= image_cap; c++) {
+    const uint4 v = runs_assemble(sm, rec_size, magic, g, 16u * c);
+    memcpy(image_out + 16u * c, &v, 16);
+  }
+  return body_end;
+}
+
 }  // extern "C"
 
 #include "merger_api.inl"
