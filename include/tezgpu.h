@@ -51,6 +51,14 @@ extern "C" {
 #define TEZGPU_RLE_OFF 0
 #define TEZGPU_RLE_ON 1
 
+/* sorter_impl = 2: the writer behind UnorderedPartitionedKVOutput (RL/common/writers/UnorderedPartitionedKVWriter.java):
+ * records are only partitioned; every partition's segment holds its records NEWEST FIRST (the per-partition chain of
+ * :459-472 walked by writePartition :688-703 -- the order the reference writes when everything fits one buffer), IFile
+ * without run-length encoding (:1092), no bytes and an all-zero index entry for a partition without records (mergeAll
+ * :1058-1144).  The comparator is ignored.  With several buffers / spills the reference's order inside a partition
+ * depends on buffer arithmetic and thread timing: parity is then the identical index + the per-partition multiset. */
+#define TEZGPU_SORTER_UNORDERED 2
+
 typedef struct tezgpu_conf {
   int32_t abi_version;                  /* TEZGPU_ABI_VERSION */
   int32_t device;                       /* CUDA ordinal */
@@ -59,10 +67,14 @@ typedef struct tezgpu_conf {
   int32_t partitioner;                  /* TEZGPU_PART_* */
   int32_t rle_policy;                   /* TEZGPU_RLE_* */
   int32_t send_empty_partition_details; /* tez.runtime.empty.partitions.info-via-events.enabled (default 1) */
-  int32_t sorter_impl;                  /* 0 = PipelinedSorter (default), 1 = DefaultSorter ("LEGACY"): only changes the AUTO RLE rule */
+  int32_t sorter_impl;                  /* 0 = PipelinedSorter (default), 1 = DefaultSorter ("LEGACY"): only changes the AUTO RLE rule,
+                                           2 = TEZGPU_SORTER_UNORDERED: UnorderedPartitionedKVWriter (partition only, no key order) */
   uint32_t fixed_key_len;               /* >0 with fixed_val_len: records are packed key||value of constant width */
   uint32_t fixed_val_len;
-  uint64_t mem_budget_bytes;            /* granted by OutputContext.requestInitialMemory; 0 = no limit */
+  uint64_t mem_budget_bytes;            /* granted by OutputContext.requestInitialMemory; 0 = no limit.  Enforced on the key+value
+                                           bytes collected since the last reset: a collect that would pass it fails with
+                                           TEZGPU_E_NOMEM and the caller spills (flush + reset), like PipelinedSorter when its
+                                           kvbuffer is full (SORT/PipelinedSorter.java:415-444) */
 } tezgpu_conf;
 
 /* counters + per-partition results; mirrors TezSpillRecord / TezIndexRecord and the ExternalSorter counters

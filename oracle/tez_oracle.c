@@ -620,6 +620,54 @@ int tzo_pipelined_sort_fixed(const tzo_sorter_conf *conf, const uint8_t *kv, uin
   return rc;
 }
 
+/* ------------------------------------------------------------------ UnorderedPartitionedKVWriter (no sort)
+ * RL/common/writers/UnorderedPartitionedKVWriter.java: records are appended to a buffer and chained per partition
+ * NEWEST FIRST (INDEX_NEXT = partitionPositions[p]; partitionPositions[p] = metaStart, :459-472); the final file walks
+ * every partition's chain from its newest record back (writePartition :688-703, mergeAll :1058-1144) through an
+ * IFile.Writer without run-length encoding (:1092).  Partitions without records are skipped: no bytes and an all-zero
+ * index entry (TezSpillRecord starts zero-filled, SORT/TezSpillRecord.java:48-52).  This restates the case in which
+ * everything fits ONE buffer (no spill thread ran): with several buffers / spills the record order inside a partition
+ * depends on buffer arithmetic and thread timing, and parity is defined on the per-partition multiset. */
+int tzo_unordered_write(const tzo_sorter_conf *conf, const uint8_t *kv, const uint64_t *key_off, const uint32_t *key_len,
+                        const uint32_t *val_len, const int32_t *partition, uint64_t n, tzo_sorter_result *res) {
+  memset(res, 0, sizeof(*res));
+  tzo_buf_init(&res->file_out);
+  tzo_buf_init(&res->index_out);
+  const int P = conf->num_partitions;
+  res->index = (int64_t *)calloc((size_t)P * 3, sizeof(int64_t));
+  int32_t *part = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n ? n : 1));
+  int64_t *next = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n ? n : 1));
+  int64_t *head = (int64_t *)malloc(sizeof(int64_t) * (size_t)P);
+  for (int p = 0; p < P; p++) head[p] = -1;
+  for (uint64_t i = 0; i < n; i++) {
+    int32_t p = partition ? partition[i]
+                          : tzo_hash_partition(tzo_key_hash(conf->cmp_kind, kv + key_off[i], key_len[i]), P);
+    if (p < 0 || p >= P) { free(part); free(next); free(head); return -1; }
+    part[i] = p;
+    next[i] = head[p];      /* INDEX_NEXT */
+    head[p] = (int64_t)i;   /* partitionPositions[p] = this record */
+    res->output_records++;
+    res->output_bytes += (int64_t)key_len[i] + val_len[i];
+  }
+  for (int p = 0; p < P; p++) {
+    if (head[p] < 0) continue;  /* "Skipping partition ... since it has no records" */
+    tzo_ifile_writer w;
+    size_t start = res->file_out.len;
+    tzo_writer_open(&w, &res->file_out, 0);
+    for (int64_t i = head[p]; i >= 0; i = next[i])
+      tzo_writer_append(&w, kv + key_off[i], (int)key_len[i], kv + key_off[i] + key_len[i], (int)val_len[i]);
+    tzo_writer_close(&w);
+    res->index[3 * p] = (int64_t)start;
+    res->index[3 * p + 1] = w.raw_len;
+    res->index[3 * p + 2] = w.comp_len;
+    res->output_bytes_with_overhead += w.raw_len;
+  }
+  res->output_bytes_physical = (int64_t)res->file_out.len;
+  tzo_spill_record_bytes(res->index, P, &res->index_out);
+  free(part); free(next); free(head);
+  return 0;
+}
+
 void tzo_sorter_result_free(tzo_sorter_result *res) {
   tzo_buf_free(&res->file_out);
   tzo_buf_free(&res->index_out);
@@ -962,7 +1010,11 @@ void tzo_gen_c3_segment(uint64_t seed, uint32_t seg_index, uint64_t target_bytes
   for (uint64_t i = 0; i < n; i++) {
     key[0] = recs[i].len;                       /* Text: vint(byte length) + UTF-8 */
     memcpy(key + 1, recs[i].w, recs[i].len);
-    put_be64(val, tzo_splitmix64(0xABCDull ^ ((uint64_t)recs[i].id << 16)));
+    /* value = f(WORD), not f(id): several ids render the same short word, and equal keys must carry equal values for
+     * the merged bytes to be independent of the order TezMerger's heap emits equal keys in (SURVEY 8c caveat ii) */
+    uint64_t hv = 0xABCDull;
+    for (int b = 0; b < recs[i].len; b++) hv = tzo_splitmix64(hv ^ recs[i].w[b]);
+    put_be64(val, hv);
     tzo_writer_append(&w, key, 1 + recs[i].len, val, 8);
   }
   tzo_writer_close(&w);

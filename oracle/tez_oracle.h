@@ -149,6 +149,12 @@ int tzo_pipelined_sort(const tzo_sorter_conf *conf, const uint8_t *kv, const uin
                        uint64_t n, tzo_sorter_result *res);
 void tzo_sorter_result_free(tzo_sorter_result *res);
 
+/* UnorderedPartitionedKVWriter (RL/common/writers/UnorderedPartitionedKVWriter.java:459-472,688-703,1058-1144), single
+ * buffer / no spill: per partition the records newest first, IFile without run-length encoding, all-zero index entries
+ * for partitions without records */
+int tzo_unordered_write(const tzo_sorter_conf *conf, const uint8_t *kv, const uint64_t *key_off, const uint32_t *key_len,
+                        const uint32_t *val_len, const int32_t *partition, uint64_t n, tzo_sorter_result *res);
+
 /* fixed-width convenience used by bench cpu_baseline: n records of (klen+vlen) bytes packed back to back */
 int tzo_pipelined_sort_fixed(const tzo_sorter_conf *conf, const uint8_t *kv, uint32_t klen, uint32_t vlen,
                              uint64_t n, tzo_sorter_result *res);

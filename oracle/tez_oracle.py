@@ -260,6 +260,30 @@ def pipelined_sort(conf, kv, key_off, key_len, val_len, partition=None):
     return _result_dict(res, conf.num_partitions)
 
 
+def unordered_write(conf, kv, key_off, key_len, val_len, partition=None):
+    """UnorderedPartitionedKVWriter restatement (single buffer, no spill): per partition newest record first, no RLE,
+    all-zero index entries for partitions without records.  Same result dict as pipelined_sort."""
+    L = lib()
+    L.tzo_unordered_write.argtypes = [C.POINTER(SorterConf), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_uint64, C.POINTER(SorterResult)]
+    L.tzo_unordered_write.restype = C.c_int
+    kv = np.ascontiguousarray(np.frombuffer(kv, dtype=np.uint8) if isinstance(kv, (bytes, bytearray)) else kv)
+    key_off = np.ascontiguousarray(key_off, dtype=np.uint64)
+    key_len = np.ascontiguousarray(key_len, dtype=np.uint32)
+    val_len = np.ascontiguousarray(val_len, dtype=np.uint32)
+    part_p = None
+    if partition is not None:
+        partition = np.ascontiguousarray(partition, dtype=np.int32)
+        part_p = partition.ctypes.data
+    res = SorterResult()
+    rc = L.tzo_unordered_write(C.byref(conf), kv.ctypes.data if kv.size else None, key_off.ctypes.data, key_len.ctypes.data,
+                               val_len.ctypes.data, part_p, len(key_off), C.byref(res))
+    if rc != 0:
+        L.tzo_sorter_result_free(C.byref(res))
+        raise IOError("tzo_unordered_write rc=%d" % rc)
+    return _result_dict(res, conf.num_partitions)
+
+
 def pipelined_sort_fixed(conf, kv, klen, vlen):
     kv = np.ascontiguousarray(kv, dtype=np.uint8)
     n = kv.size // (klen + vlen)

@@ -279,3 +279,29 @@ def test_sorter_handle_reset_reuses_allocations():
             out, index_bytes, _, _ = s.flush_to_memory()
             exp = O.pipelined_sort_fixed(O.sorter_conf(4), kv, 16, 64)
             assert bytes(out) == exp["file_out"] and index_bytes == exp["index_out"]
+
+
+def test_sort_memory_budget_is_enforced_and_spill_recovers():
+    """tezgpu_conf.mem_budget_bytes (the memory ExternalSorter was granted): collecting past it is TEZGPU_E_NOMEM, the
+    caller spills (flush + reset) and goes on -- the host layer's multi-spill path rests on exactly this."""
+    kv = O.gen_c2(0, 3000, seed=9)
+    with T.GpuSorter(4, fixed=(16, 64), mem_budget=2000 * 80) as s:
+        s.collect_fixed(kv[:1500 * 80])
+        with pytest.raises(IOError) as ei:
+            s.collect_fixed(kv[1500 * 80:])
+        assert ei.value.code == T.E_NOMEM and "budget" in str(ei.value)
+        out1, _, _, _ = s.flush_to_memory()
+        s.reset()
+        s.collect_fixed(kv[1500 * 80:])
+        out2, _, _, _ = s.flush_to_memory()
+    assert bytes(out1) == O.pipelined_sort_fixed(O.sorter_conf(4), kv[:1500 * 80], 16, 64)["file_out"]
+    assert bytes(out2) == O.pipelined_sort_fixed(O.sorter_conf(4), kv[1500 * 80:], 16, 64)["file_out"]
+    recs = [(b"k%04d" % i, b"v" * 50) for i in range(100)]
+    kvb, ko, vo, vl = _pack(recs)
+    with T.GpuSorter(2, mem_budget=3000) as s:
+        s.collect(kvb[:int(vo[49] + vl[49])], ko[:50], vo[:50], vl[:50])
+        with pytest.raises(IOError, match="budget"):
+            s.collect(kvb[int(ko[50]):], ko[50:] - ko[50], vo[50:] - ko[50], vl[50:])
+    with T.GpuSorter(2, mem_budget=10) as s:           # a first batch larger than the whole budget is still taken
+        s.collect(kvb, ko, vo, vl)
+        assert s.flush_to_memory()[3]["output_records"] == 100

@@ -650,6 +650,9 @@ class Merger {
     r.num_partitions = pipe.state.rec.num_partitions;
     r.pbits = pipe.state.rec.pbits;
     pipe.state.rec = r;
+    // the record view changed (explicit offsets instead of the run table): the emit must lay its tiles out again --
+    // tile sizes depend on the kernel that serves the view (set_fixed_layout)
+    pipe.state.spec_layout = false;
     arrays_ready = true;
   }
 

@@ -141,6 +141,7 @@ class SortPipeline {
     e.crc = DeviceConstants::get(conf.device).d_crc;
     e.rle = rle;
     e.send_empty = conf.send_empty_partition_details;
+    e.unordered = conf.sorter_impl == TEZGPU_SORTER_UNORDERED;
     e.merge_mode = merge_mode ? 1 : 0;
     e.check_same = merge_check_same;
     e.P = conf.num_partitions;
@@ -197,6 +198,7 @@ class SortPipeline {
     if (conf.rle_policy == TEZGPU_RLE_ON) rle = 1;
     else if (conf.rle_policy == TEZGPU_RLE_OFF) rle = 0;
     else rle = (conf.sorter_impl == 1) ? 0 : ((double)state.dup_count > 0.1 * (double)rec.n);
+    if (conf.sorter_impl == TEZGPU_SORTER_UNORDERED) rle = 0;   // Writer(..., codec, null, null): no run-length encoding (:1092)
     emit_phase(rle, false, d_out, out_cap, out_len, index, stats);
   }
 
@@ -210,6 +212,8 @@ class SortPipeline {
     rec.hash_partition = conf.partitioner == TEZGPU_PART_HASH;
     rec.num_partitions = P;
     rec.pbits = pbits;
+    const bool unordered = conf.sorter_impl == TEZGPU_SORTER_UNORDERED;
+    rec.unordered = unordered ? 1 : 0;
     TG_CHECK(rec.hash_partition || rec.partition || rec.use_runs || n == 0 || P == 1, TEZGPU_E_INVALID, "partition ids required (partitioner=GIVEN)");
     int launches = 0;
     state.have_bounds = state.spec_layout = false;
@@ -237,7 +241,7 @@ class SortPipeline {
     uint32_t *order = valsA.as<uint32_t>();
 
     uint32_t sym_npos = 0;
-    if (n && !rec.fixed && !(getenv("TEZGPU_NO_SYM") && atoi(getenv("TEZGPU_NO_SYM")))) {
+    if (n && !rec.fixed && !unordered && !(getenv("TEZGPU_NO_SYM") && atoi(getenv("TEZGPU_NO_SYM")))) {
       // ---------------- alphabet-compressed sort word (SymTable, sorter_kernels.cuh): which byte values occur at the
       // first content positions -> per-position ranks, packed while they fit the (32 - pbits)-bit key field
       sym_sets.ensure(SYM_MAX_POS * 8 * 4);
@@ -296,9 +300,21 @@ class SortPipeline {
       ws.tile_state_words = radix_tile_state_words<uint32_t>(n, 4);
       tile_state.ensure(ws.tile_state_words * 4);
       ws.tile_state = tile_state.as<uint32_t>();
+      // unordered: only the passes that cover the partition bits (the top pbits of the word); none when P == 1 -- the
+      // first pass is still needed then, to produce the identity index array
+      uint32_t pass_mask = 0xF;
+      if (unordered) {
+        pass_mask = 0;
+        for (int q = 0; q < 4; q++) if (8 * q + 8 > 32 - pbits) pass_mask |= 1u << q;
+        if (!pass_mask) pass_mask = 1;
+      }
       int done = radix_sort_passes<uint32_t>(stream, ws, keysA.as<uint32_t>(), keysB.as<uint32_t>(), valsA.as<uint32_t>(),
-                                             valsB.as<uint32_t>(), n, 0, 4, 0xF, true, &launches);
+                                             valsB.as<uint32_t>(), n, 0, 4, pass_mask, true, &launches);
       if (done & 1) { K = keysB.as<uint32_t>(); order = valsB.as<uint32_t>(); }
+      if (unordered) {
+        k_flip_order<<<(uint32_t)div_up(n, 256), 256, 0, stream>>>(order, n);
+        launches++;
+      }
       timer.mark(stream);
 
       // ---------------- ties: records whose sort words collide are ordered by the rest of the key.
@@ -309,8 +325,9 @@ class SortPipeline {
       const uint32_t depth0 = rec.sym ? sym_npos : (uint32_t)((32 - pbits) / 8);
       int per_sm_tf = 0;
       TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tf, k_tie_fix, TIEFIX_THREADS, 0));
-      k_tie_fix<<<(uint32_t)std::min<uint64_t>(div_up(n, TIEFIX_TILE), (uint64_t)num_sms * std::max(per_sm_tf, 1)), TIEFIX_THREADS, 0, stream>>>(
-          rec, K, order, n, depth0, same.as<uint8_t>(), d_dups(), d_large(), d_ties());
+      if (!unordered)   // no comparator on an unordered edge: records of a partition keep their (reversed arrival) order
+        k_tie_fix<<<(uint32_t)std::min<uint64_t>(div_up(n, TIEFIX_TILE), (uint64_t)num_sms * std::max(per_sm_tf, 1)), TIEFIX_THREADS, 0, stream>>>(
+            rec, K, order, n, depth0, same.as<uint8_t>(), d_dups(), d_large(), d_ties());
       const uint32_t *d_m_ptr = reinterpret_cast<const uint32_t *>(d_ties());
       k_part_bounds<<<(uint32_t)div_up((uint64_t)P + 1, 256), 256, 0, stream>>>(K, n, P, pbits, part_start.as<uint32_t>());
       launches += 2;

@@ -85,6 +85,8 @@ struct Records {
   int use_runs;   // fixed mode: records are addressed through `runs` instead of index * stride / key_off
   RunTable runs;
   const SymTable *sym;  // optional alphabet-compressed sort word (variable-length keys)
+  int unordered;        // UnorderedPartitionedKVWriter: no key order; the sort word is the partition alone and record i is
+                        // staged at position n-1-i, so the stable sort leaves every partition newest record first
 };
 
 __device__ __forceinline__ void record_lookup(const Records &r, uint32_t i, uint64_t &koff, uint32_t &klen,
@@ -184,8 +186,9 @@ __global__ void __launch_bounds__(256) k_stage(Records r, uint32_t *__restrict__
       atomicOr(error_flag, 1);  // "Illegal partition" (PipelinedSorter.java:410-413)
       p = 0;
     }
+    if (r.unordered) prefix = 0;
     uint32_t K = r.pbits ? (((uint32_t)p << (32 - r.pbits)) | (prefix >> r.pbits)) : prefix;
-    keys_out[i] = K;
+    keys_out[r.unordered ? r.n - 1u - i : i] = K;
 #pragma unroll
     for (int q = 0; q < 4; q++) atomicAdd(&s_hist[q * RADIX + ((K >> (8 * q)) & 0xFF)], 1u);
   }
@@ -616,6 +619,12 @@ __global__ void __launch_bounds__(SCAN_THREADS)
   }
 }
 
+// unordered mode: the sort ran over positions n-1-i; turn them back into record indices
+__global__ void k_flip_order(uint32_t *__restrict__ order, uint32_t n) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n) order[r] = n - 1u - order[r];
+}
+
 // ------------------------------------------------------------------------------------------------ layout
 // part_start[p] = first sorted position of partition p (p in [0, P]); lower_bound over the sorted sort words
 __global__ void k_part_bounds(const uint32_t *__restrict__ K, uint32_t n, int P, int pbits,
@@ -653,6 +662,7 @@ struct EmitParams {
   int merge_mode;      // TezMerger.writeFile semantics: isSameKey() records go through IFile.REPEAT_KEY
   int check_same;      // merge_mode: MergeQueue.checkForSameKeys (SORT/TezMerger.java:563-573,597-652)
   int send_empty;
+  int unordered;       // UnorderedPartitionedKVWriter.mergeAll: partitions without records get an all-zero index entry
   int P;
 };
 
@@ -722,7 +732,7 @@ __global__ void __launch_bounds__(1024)
         body = e.rec_off ? (e.rec_off[b] - e.rec_off[a]) : (uint64_t)cnt * e.rec_size;
         seglen = 4 + body + 2 + 4;
         tiles = (cnt + e.recs_per_tile - 1) / e.recs_per_tile;
-      } else if (!e.send_empty) {
+      } else if (!e.send_empty && !e.unordered) {
         seglen = 10;
       }
     }
@@ -749,7 +759,7 @@ __global__ void __launch_bounds__(1024)
       uint64_t start = cb + wb + ib - vb;
       seg_start[p] = start;
       tile_start[p] = (uint32_t)(ct + wt + it - vt);
-      index[3 * p + 0] = (int64_t)start;
+      index[3 * p + 0] = (e.unordered && !seglen) ? 0 : (int64_t)start;
       index[3 * p + 1] = seglen ? (int64_t)(seglen - 4) : 0;  // rawLength = header + body + EOF, no checksum
       index[3 * p + 2] = (int64_t)seglen;                     // partLength (uncompressed) = rawLength + 4
     }

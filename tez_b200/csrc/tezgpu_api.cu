@@ -164,6 +164,17 @@ int32_t tezgpu_sorter_collect_batch(tezgpu_sorter *h, const uint8_t *kv, uint64_
            "partition ids must be given for all batches or none");
   TG_CHECK(partition || h->pipe.conf.partitioner == TEZGPU_PART_HASH, TEZGPU_E_INVALID,
            "partition ids required (partitioner=GIVEN)");
+  {
+    // the sort memory granted to this output (ExternalSorter.getInitialMemoryRequirement, SORT/ExternalSorter.java:330-347;
+    // PipelinedSorter spills when its kvbuffer is full, :415-444): past it the caller must spill -- flush + reset --
+    // first.  A first batch larger than the whole budget is still taken (the reference writes such records through).
+    uint64_t add = 0;
+    for (uint32_t i = 0; i < n; i++) add += (uint64_t)(val_off[i] - key_off[i]) + val_len[i];
+    const uint64_t budget = h->pipe.conf.mem_budget_bytes;
+    TG_CHECK(budget == 0 || h->n == 0 || h->payload_bytes + add <= budget, TEZGPU_E_NOMEM,
+             "sort memory budget exceeded (" + std::to_string(h->payload_bytes + add) + " > " + std::to_string(budget) +
+                 " bytes): spill (flush + reset) before collecting more");
+  }
   cudaStream_t st = h->pipe.stream;
   TG_CUDA(cudaSetDevice(h->pipe.conf.device));
   const uint64_t base = align_up(h->kv_bytes, 16);  // every batch starts 16-byte aligned
@@ -208,9 +219,15 @@ int32_t tezgpu_sorter_collect_fixed(tezgpu_sorter *h, const uint8_t *kv, const i
            "partition ids must be given for all batches or none");
   TG_CHECK(partition || h->pipe.conf.partitioner == TEZGPU_PART_HASH, TEZGPU_E_INVALID,
            "partition ids required (partitioner=GIVEN)");
+  const uint64_t stride = (uint64_t)h->klen + h->vlen;
+  {
+    const uint64_t budget = h->pipe.conf.mem_budget_bytes;
+    TG_CHECK(budget == 0 || h->n == 0 || (h->n + n) * stride <= budget, TEZGPU_E_NOMEM,
+             "sort memory budget exceeded (" + std::to_string((h->n + n) * stride) + " > " + std::to_string(budget) +
+                 " bytes): spill (flush + reset) before collecting more");
+  }
   cudaStream_t st = h->pipe.stream;
   TG_CUDA(cudaSetDevice(h->pipe.conf.device));
-  const uint64_t stride = (uint64_t)h->klen + h->vlen;
   h->d_kv.grow_preserve((h->n + n) * stride + 32, h->n * stride, st);
   if (partition) h->d_part.grow_preserve((h->n + n) * 4, h->n * 4, st);
   TG_CUDA(cudaMemcpyAsync(h->d_kv.as<uint8_t>() + h->n * stride, kv, n * stride, cudaMemcpyHostToDevice, st));

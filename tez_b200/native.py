@@ -17,7 +17,7 @@ def _ptr(a):
 
 
 def make_conf(num_partitions, comparator=CMP_BYTES, partitioner=PART_HASH, rle_policy=RLE_AUTO, send_empty=True,
-              fixed=None, device=0, legacy=False, mem_budget=0):
+              fixed=None, device=0, legacy=False, mem_budget=0, unordered=False):
     c = Conf()
     c.abi_version = ABI_VERSION
     c.device = device
@@ -26,7 +26,7 @@ def make_conf(num_partitions, comparator=CMP_BYTES, partitioner=PART_HASH, rle_p
     c.partitioner = partitioner
     c.rle_policy = rle_policy
     c.send_empty_partition_details = 1 if send_empty else 0
-    c.sorter_impl = SORTER_LEGACY if legacy else SORTER_PIPELINED
+    c.sorter_impl = SORTER_UNORDERED if unordered else (SORTER_LEGACY if legacy else SORTER_PIPELINED)
     c.fixed_key_len, c.fixed_val_len = fixed if fixed else (0, 0)
     c.mem_budget_bytes = mem_budget
     return c
