@@ -362,6 +362,38 @@ def single_gpu(args):
     return 0
 
 
+def config1(args):
+    """BASELINE config 1: OrderedWordCount (tez-examples OrderedWordCount.java:124-180), ~100 MB of synthetic text, 4
+    tokenizer tasks, 4 reducers, local mode: both ordered edges through the plugin mirror (C++ host layer over the CUDA
+    library, real files / indexes / counters), beside the same job through the CPU restatement of PipelinedSorter +
+    TezMerger -- the configuration the reference itself runs on a CPU.  tools/owc_bench.cc drives both arms and checks
+    the job's known answer."""
+    import tempfile
+    exe = os.path.join(ROOT, "tools", "owc_bench")
+    if not os.path.exists(exe):
+        import __graft_entry__
+        __graft_entry__.build_tools()
+    mb, toks, reds = args.c1_text_mb, 4, 4
+    with tempfile.TemporaryDirectory() as wd:
+        g = json.loads(subprocess.check_output([exe, "gpu", str(mb), str(toks), str(reds), wd], text=True).strip().splitlines()[-1])
+        c = json.loads(subprocess.check_output([exe, "cpu", str(mb), str(toks), str(reds), wd], text=True).strip().splitlines()[-1])
+    line = {"metric": METRIC.replace("(16B key / 64B val)", "(OrderedWordCount, both ordered edges)"), "value": round(g["kv_gbs"], 4),
+            "unit": "GB/s", "n_gpus": 1, "steps": 1, "warmup": 1, "ms_per_step": round(g["seconds"] * 1e3, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "BASELINE config 1: OrderedWordCount, %d MB of synthetic text (Zipf(1.0) over 1000 words), %d tokenizer "
+                                   "tasks, %d reducers, local mode, files + indexes + counters as Tez" % (mb, toks, reds),
+                       "records": g["records"], "timing": "wall clock of the shuffle-bound part of the job (sort, spill files, merge, "
+                                                          "grouping, second ordered edge), host buffers and local files inside"},
+            "e2e": {"value": round(g["kv_gbs"], 4), "unit": "GB/s", "note": "the job IS the end-to-end path: records enter through "
+                    "KeyValuesWriter.write and leave through KeyValuesReader"},
+            "gpu_launches": None, "roofline": None,
+            "parity": {"known_answer_checked_both_arms": bool(g["answer_checked"] and c["answer_checked"])},
+            "cpu_baseline": {"value": round(c["kv_gbs"], 5), "unit": "GB/s", "cores": 2, "kind": "port",
+                             "sample": "the whole job through the CPU restatement (PipelinedSorter with sort.threads=2, TezMerger), %.2f s" % c["seconds"]}}
+    print(json.dumps(line))
+    return 0
+
+
 def config3(args):
     """BASELINE config 3: k-way TezMerger of sorted spill segments with variable-length Text keys on one GPU.
     Inputs: --c3-segments IFile segments of --c3-segment-mb MiB (SURVEY 8d generator: words from a 2^24-id space, length
@@ -466,7 +498,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-g1-pipeline", action="store_true")
-    ap.add_argument("--config", type=int, default=2, help="2 (default, the driver's line) or 3 (k-way merge, one GPU)")
+    ap.add_argument("--config", type=int, default=2,
+                    help="2 (default, the driver's line), 1 (OrderedWordCount through the plugin mirror) or 3 (k-way merge)")
+    ap.add_argument("--c1-text-mb", type=int, default=100)
     ap.add_argument("--c3-segments", type=int, default=256)
     ap.add_argument("--c3-segment-mb", type=int, default=64)
     ap.add_argument("--c3-cpu-segments", type=int, default=16)
@@ -478,6 +512,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return reference_arm(args)
+    if args.config == 1:
+        return config1(args)
     if args.config == 3:
         return config3(args)
     if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
