@@ -186,7 +186,12 @@ def reference_arm(args):
     return 0
 
 
-def workload_config(gpus, records):
+def workload_config(gpus, records, config=4):
+    if config == 5:
+        return {"workload": "BASELINE config 5 shape (weak): %d records per GPU, Zipf(1.1) keys over 2^32 ids, 16B key / 4 KB value, "
+                            "256 partitions, owner(p) = p*N/P, NVLink pull, per-GPU batched merge of run-length encoded segments" % records,
+                "records_per_gpu": records, "partitions": 256, "parallelism": "partition-sharded x%d" % gpus,
+                "l2": "inputs larger than L2, no flush needed"}
     if gpus == 1:
         return {"workload": "BASELINE config 2: %d records, 16B key / 64B value, 64 partitions, HashPartitioner, "
                             "TezBytesComparator, IFile + CRC32 out" % records,
@@ -499,7 +504,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-g1-pipeline", action="store_true")
     ap.add_argument("--config", type=int, default=2,
-                    help="2 (default, the driver's line), 1 (OrderedWordCount through the plugin mirror) or 3 (k-way merge)")
+                    help="2 (default, the driver's line), 1 (OrderedWordCount through the plugin mirror), 3 (k-way merge) or "
+                         "5 (Zipf keys, 4 KB values, 256 partitions; any --gpus)")
     ap.add_argument("--c1-text-mb", type=int, default=100)
     ap.add_argument("--c3-segments", type=int, default=256)
     ap.add_argument("--c3-segment-mb", type=int, default=64)
@@ -507,7 +513,10 @@ def main():
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.records is None:
-        args.records = 100_000_000 if (args.gpus == 1 and world == 1) else 125_000_000
+        if args.config == 5:
+            args.records = 4_000_000      # 16.4 GB of records per GPU
+        else:
+            args.records = 100_000_000 if (args.gpus == 1 and world == 1) else 125_000_000
     if args.warmup < 3 and args.impl != "reference":
         args.warmup = 3
     if args.impl == "reference":
@@ -516,15 +525,18 @@ def main():
         return config1(args)
     if args.config == 3:
         return config3(args)
-    if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    if args.config != 5 and args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
         return single_gpu(args)
+    if args.config == 5 and "RANK" not in os.environ:      # config 5 on one GPU without torchrun: a world of one
+        os.environ.update({"RANK": "0", "WORLD_SIZE": "1", "LOCAL_RANK": "0", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "29533"})
     from tez_b200 import multigpu_bench
 
     def verify_partition(runs, merged):
         # the checker (test infrastructure, outside the timed region): TezMerger restatement over the same runs
+        import numpy as np
         from oracle import tez_oracle as O
-        exp = O.merge(runs, O.CMP_BYTES, factor=100)["ifile"]
-        assert merged == exp, "merged partition differs from the oracle's TezMerger output"
+        exp, _, _ = O.merge_ifile(runs, O.CMP_BYTES, factor=100)
+        assert np.array_equal(np.frombuffer(merged, dtype=np.uint8), exp), "merged partition differs from the oracle's TezMerger output"
 
     return multigpu_bench.run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores, verify_partition)
 

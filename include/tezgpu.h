@@ -185,6 +185,10 @@ int32_t tezgpu_merge_reopen(tezgpu_merger *m, const tezgpu_segment *segs, uint32
  * merger.needsRLE() here AND as the writer's rle (SORT/PipelinedSorter.java:797-814).  Call before next_batch / write. */
 int32_t tezgpu_merge_set_check_for_same_keys(tezgpu_merger *m, int32_t check_for_same_keys);
 /* total records / key+value bytes of the merged stream */
+/* diagnostics: how the last open / reopen located the records -- mode 0: fixed framing, records addressed in place
+ * (no parse); 1: parallel window parser (rounds = counting rounds it took); 2: sequential walker (one lane per
+ * segment: the fallback when the window parser does not converge or meets a malformed record) */
+int32_t tezgpu_merge_parse_info(tezgpu_merger *m, int32_t *mode, int32_t *rounds);
 int32_t tezgpu_merge_counts(tezgpu_merger *m, uint64_t *records, uint64_t *kv_bytes);
 /* replaces the next()/getKey()/getValue()/isSameKey() loop: fills up to idx_cap records (key||value bytes appended to
  * out_kv, at most cap bytes); *n = 0 at end of stream */
@@ -256,6 +260,9 @@ uint32_t tezgpu_debug_crc_emulate(const uint8_t *body, uint64_t len, uint32_t pi
 uint32_t tezgpu_debug_assemble_emulate(const uint8_t *stage, uint32_t nr, uint32_t stride, const uint8_t *hdr,
                                        uint32_t hdr_len, uint32_t lead, int32_t first, int32_t last, uint8_t *image_out,
                                        uint32_t image_cap);
+
+/* diagnostics: host-side run of the chunk-interleaved CRC fold of the emit / verify kernels (ilp: two-deep form) */
+uint32_t tezgpu_debug_chunk_fold_emulate(const uint8_t *data, uint32_t nchunks, int32_t ilp);
 
 uint32_t tezgpu_debug_runs_assemble_emulate(const uint8_t *staging, uint32_t staging_len, const uint32_t *src, uint32_t nr,
                                             uint32_t rec_size, uint32_t lead, int32_t first, int32_t last,

@@ -16,6 +16,18 @@ def test_tiled_crc_algebra_matches_zlib():
                 assert L.tezgpu_debug_crc_emulate(d, n, piece, lead) == zlib.crc32(d), (n, piece, lead)
 
 
+def test_chunk_fold_two_deep_form_matches_zlib():
+    """crc32.cuh CrcChunkFold: the two-maps-deep chunk update (and the x^(-128*(T-1)) correction it needs, which rests
+    on x having order 2^32-1 modulo the CRC-32 polynomial) gives the same remainder as the textbook chain and as zlib."""
+    L = _lib.load()
+    rng = random.Random(7)
+    for nchunks in [1, 2, 31, 32, 33, 255, 256, 257, 511, 512, 513, 1000, 1290, 2048, 5000]:
+        d = bytes(rng.getrandbits(8) for _ in range(16 * nchunks))
+        raw = zlib.crc32(d) ^ zlib.crc32(bytes(16 * nchunks))       # linear part: init 0, no final xor
+        assert L.tezgpu_debug_chunk_fold_emulate(d, nchunks, 0) == raw, nchunks
+        assert L.tezgpu_debug_chunk_fold_emulate(d, nchunks, 1) == raw, nchunks
+
+
 def test_segment_table_fast_path_matches_ctypes_layout():
     """GpuMerger builds the tezgpu_segment table through numpy when there are many device-resident runs; the bytes must
     equal what the ctypes structure assignment produces (include/tezgpu.h: data, len, flags, partition)."""

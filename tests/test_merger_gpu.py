@@ -254,6 +254,8 @@ def test_config3_shape_text_merge_bit_exact(nseg, seg_kb, id_bits):
     exp, n, _ = O.merge_ifile(segs, O.CMP_TEXT, factor=100)
     with T.GpuMerger([s.tobytes() for s in segs], comparator=T.CMP_TEXT) as m:
         assert m.counts()[0] == n == sum(nrec)
+        mode, rounds = m.parse_info()
+        assert mode == 1 and rounds <= 3, (mode, rounds)   # the window parser, not the sequential walker
         seg, raw, part, st = m.write_ifile()
     assert part == exp.size
     assert np.array_equal(np.frombuffer(seg, dtype=np.uint8), exp)
@@ -263,3 +265,90 @@ def test_config3_shape_text_merge_bit_exact(nseg, seg_kb, id_bits):
         m.set_check_for_same_keys(False)
         seg2, _, part2, _ = m.write_ifile()
     assert np.array_equal(np.frombuffer(seg2, dtype=np.uint8), exp2)
+
+
+@pytest.mark.parametrize("shape", ["binary_values", "rle_runs", "long_records", "ff_bytes"])
+def test_window_parser_on_multi_window_segments(shape):
+    """parse_windows.cuh: segments of many 32 KiB windows whose bytes invite wrong walks -- random binary values (every
+    byte value is a plausible vint), long run-length encoded runs (windows that begin inside a run), records longer
+    than a window, values full of 0xFF (EOF look-alikes).  Whatever route open() takes (window parser, or the sequential
+    walker when it does not converge) the merge must equal TezMerger's; for the first two shapes the window parser
+    itself must converge."""
+    rng = random.Random(zlib.crc32(shape.encode()))
+    rs = np.random.default_rng(11)
+    segs = []
+    for sidx in range(5):
+        recs = []
+        if shape == "binary_values":
+            keys = sorted({rng.getrandbits(40).to_bytes(5, "big") for _ in range(30000)})
+            for k in keys:
+                recs.append((k, rs.integers(0, 256, 1 + k[4] % 23, dtype=np.uint8).tobytes() if sidx == 0 else bytes([k[3]]) * (1 + k[4] % 23)))
+            # values must be a function of the key across segments: segment 0 keeps private keys
+            if sidx == 0:
+                recs = [(b"\x00" + k, v) for k, v in recs]
+            else:
+                recs = [(b"\x01" + k, v) for k, v in recs]
+        elif shape == "rle_runs":
+            keys = sorted({rng.getrandbits(24).to_bytes(3, "big") + bytes([sidx]) for _ in range(300)})
+            for k in keys:
+                for _ in range(1 + (k[0] * 7) % 900):       # runs of up to 900 repeats (tens of KB: whole windows inside one run)
+                    recs.append((k, (zlib.crc32(k) & 0xFFFFFF).to_bytes(3, "big") * (1 + k[1] % 9)))
+        elif shape == "long_records":
+            keys = sorted({rng.getrandbits(32).to_bytes(4, "big") + bytes([sidx]) for _ in range(40)})
+            for k in keys:
+                recs.append((k, bytes([k[0]]) * (20000 + 1000 * (k[1] % 50))))
+        else:
+            keys = sorted({b"\xff" * (1 + rng.randint(0, 3)) + rng.getrandbits(32).to_bytes(4, "big") + bytes([sidx]) for _ in range(20000)})
+            for k in keys:
+                recs.append((k, b"\xff" * (2 + k[-2] % 30)))
+        segs.append(O.write_ifile(recs, rle=True)[0])
+    assert min(len(x) for x in segs) > 3 * 32768
+    exp = O.merge(segs, O.CMP_BYTES, factor=100)
+    with T.GpuMerger(segs, comparator=T.CMP_BYTES) as m:
+        mode, rounds = m.parse_info()
+        assert mode in (1, 2)
+        if shape in ("binary_values", "ff_bytes"):
+            assert mode == 1, (mode, rounds)
+        assert m.counts()[0] == len(exp["records"])
+        seg, raw, part, _ = m.write_ifile()
+    assert seg == exp["ifile"]
+
+
+@pytest.mark.parametrize("val_len,n", [(4096, 6000), (256, 60000)])
+def test_config5_shape_zipf_keys_sort_and_merge_bit_exact(val_len, n):
+    """BASELINE config 5 shape: Zipf(1.1) keys (one key holds ~7 % of the records), large values = f(key), so the map side
+    turns run-length encoding on, the reduce side parses RLE segments of multi-KB records, meets tie groups of thousands
+    of equal keys, and writes REPEAT_KEY runs.  Map side vs the PipelinedSorter oracle, reduce side vs TezMerger."""
+    from tez_b200 import synth
+    P, G = 8, 3
+    outs = []
+    for g in range(G):
+        kv = synth.gen_c5(g * n, n, seed=5, val_len=val_len, device="cuda").cpu().numpy()
+        exp = O.pipelined_sort_fixed(O.sorter_conf(P), kv, 16, val_len)
+        with T.GpuSorter(P, fixed=(16, val_len)) as s:
+            s.collect_fixed(kv)
+            out, index_bytes, index, st = s.flush_to_memory()
+        assert st["rle_used"] and exp["rle_used"]
+        assert np.array_equal(np.frombuffer(bytes(out), dtype=np.uint8), np.frombuffer(exp["file_out"], dtype=np.uint8))
+        assert index_bytes == exp["index_out"]
+        outs.append((bytes(out), index))
+    segs, parts = [], []
+    for g in range(G):
+        for p in range(P):
+            a, raw, ln = (int(x) for x in outs[g][1][p])
+            if ln:
+                segs.append(outs[g][0][a:a + ln])
+                parts.append(p)
+    import torch
+    with T.GpuMerger(segs, comparator=T.CMP_BYTES, partitions=parts, num_partitions=P, fixed=(16, val_len)) as m:
+        cap = m.output_bound()
+        d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        nbytes, index, st = m.write_partitions_device(d_out.data_ptr(), cap)
+        merged = d_out[:nbytes].cpu().numpy()
+    for p in range(P):
+        mine = [sg for sg, q in zip(segs, parts) if q == p]
+        a, raw, ln = (int(x) for x in index[p])
+        if not mine:
+            continue
+        exp, _, _ = O.merge_ifile(mine, O.CMP_BYTES, factor=100)
+        assert ln == exp.size and np.array_equal(merged[a:a + ln], exp), "partition %d" % p

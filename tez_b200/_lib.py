@@ -57,11 +57,13 @@ SYMBOLS = [
     ("tezgpu_sorter_sort_device_fixed", C.c_int32, [_V, _V, _V, C.c_uint64, _V, C.c_uint64, _P(C.c_uint64), _V, _P(Stats)]),
     ("tezgpu_sorter_stream", _V, [_V]),
     ("tezgpu_debug_crc_emulate", C.c_uint32, [_V, C.c_uint64, C.c_uint32, C.c_uint32]),
+    ("tezgpu_debug_chunk_fold_emulate", C.c_uint32, [_V, C.c_uint32, C.c_int32]),
     ("tezgpu_debug_runs_assemble_emulate", C.c_uint32, [_V, C.c_uint32, _V, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _V, C.c_uint32]),
     ("tezgpu_debug_assemble_emulate", C.c_uint32, [_V, C.c_uint32, C.c_uint32, _V, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _V, C.c_uint32]),
     ("tezgpu_merge_open", C.c_int32, [_P(Conf), _P(Segment), C.c_uint32, _P(_V)]),
     ("tezgpu_merge_reopen", C.c_int32, [_V, _P(Segment), C.c_uint32]),
     ("tezgpu_merge_set_check_for_same_keys", C.c_int32, [_V, C.c_int32]),
+    ("tezgpu_merge_parse_info", C.c_int32, [_V, _V, _V]),
     ("tezgpu_merge_counts", C.c_int32, [_V, _P(C.c_uint64), _P(C.c_uint64)]),
     ("tezgpu_merge_next_batch", C.c_int32, [_V, _V, C.c_uint64, _P(KvIndex), C.c_uint32, _P(C.c_uint32)]),
     ("tezgpu_merge_write_ifile", C.c_int32, [_V, C.c_char_p, _V, C.c_uint64, C.c_int32, _P(C.c_int64), _P(C.c_int64), _P(Stats)]),

@@ -32,6 +32,8 @@ struct CrcTables {
   uint32_t adv32[4][256];   // multiply-by-x^(32*32) byte tables (second-level fold of the per-thread partials)
   uint32_t advc[4][256];    // multiply-by-x^(32*(4*stride-3)): 16-byte-chunk interleave (fused CRC + write-out)
   uint32_t adv128[4][256];  // multiply-by-x^(32*128): second-level fold of chunk-interleaved partials
+  uint32_t advc2[4][256];   // multiply-by-x^(32*(4*stride-1)): the "skip" of advc composed with two "next word" steps
+  uint32_t einv;            // x^(-128*(stride-1)): undoes the skip the two-deep chunk fold applies after a thread's LAST chunk
   uint32_t pow_word[512];   // x^(32*j), j < 512
   uint32_t pow0[4096];      // x^(8*a)
   uint32_t pow1[4096];      // x^(8*4096*a)
@@ -48,6 +50,23 @@ static inline uint32_t crc_host_xpow8(uint64_t nbytes) {
     nbytes >>= 1;
   }
   return result;
+}
+
+// x^nbits mod P by square-and-multiply
+static inline uint32_t crc_host_xpow_bits(uint64_t nbits) {
+  uint32_t result = 0x80000000u;  // x^0
+  uint32_t base = 0x40000000u;    // x^1
+  while (nbits) {
+    if (nbits & 1) result = crc_multmodp(result, base);
+    base = crc_multmodp(base, base);
+    nbits >>= 1;
+  }
+  return result;
+}
+// x^(-nbits) mod P: the CRC-32 polynomial is primitive, x has order 2^32 - 1 (checked on the CPU: tests/test_abi_cpu.py)
+static inline uint32_t crc_host_xpow_bits_inv(uint64_t nbits) {
+  const uint64_t ord = 0xFFFFFFFFull;
+  return crc_host_xpow_bits((ord - nbits % ord) % ord);
 }
 
 static inline void crc_build_tables(CrcTables &t, int stride_words) {
@@ -71,6 +90,10 @@ static inline void crc_build_tables(CrcTables &t, int stride_words) {
       t.advc[k][b] = crc_multmodp(b << (8 * k), xc);
       t.adv128[k][b] = crc_multmodp(b << (8 * k), x128);
     }
+  const uint32_t xc2 = crc_host_xpow8((uint64_t)4 * (uint64_t)(4 * stride_words - 1));
+  for (int k = 0; k < 4; k++)
+    for (uint32_t b = 0; b < 256; b++) t.advc2[k][b] = crc_multmodp(b << (8 * k), xc2);
+  t.einv = crc_host_xpow_bits_inv((uint64_t)128 * (uint64_t)(stride_words - 1));
   for (int j = 0; j < 512; j++) t.pow_word[j] = crc_host_xpow8((uint64_t)4 * (uint64_t)j);
   uint32_t s0 = crc_host_xpow8(1), s1 = crc_host_xpow8(4096), s2 = crc_host_xpow8(1ull << 24);
   t.pow0[0] = t.pow1[0] = t.pow2[0] = 0x80000000u;
@@ -106,6 +129,52 @@ struct WarpLinearMap {
     uint32_t r5 = __shfl_sync(0xffffffffu, t[5], (int)(x >> 25));
     uint32_t r6 = __shfl_sync(0xffffffffu, t[6], (int)(x >> 30));
     return (r0 ^ r1 ^ r2) ^ (r3 ^ r4 ^ r5) ^ r6;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------- chunk fold
+// Per-thread update of the chunk-interleaved checksum for one 16-byte chunk (w0..w3): with W = "* x^32" (next word)
+// and S = "* x^(32*(4T-3))" (skip to this thread's next chunk) the textbook update is the dependent chain
+//        c' = S( W( W( W(c ^ w0) ^ w1 ) ^ w2 ) ^ w3 )            -- four table maps deep,
+// which left the emit kernels waiting on their own arithmetic (ncu: "wait" + short-scoreboard stalls with 5 warps per
+// scheduler).  Linearity gives the same value two maps deep:
+//        u = W(c ^ w0) ^ w1,   v = W(w2) ^ w3,   c' = (S W^2)(u) ^ S(v)
+// -- same number of look-ups (28 SHFL), half the latency, the two halves independent.  The thread's LAST chunk used to
+// end with W instead of S; here S is applied there too and the constant factor x^(128*(T-1)) it adds to every partial
+// is divided out once, in the per-lane alignment multiplier of the final fold (CrcTables::einv).
+#ifndef TEZGPU_CRC_ILP
+#define TEZGPU_CRC_ILP 1
+#endif
+struct CrcChunkFold {
+  WarpLinearMap w, s;
+#if TEZGPU_CRC_ILP
+  WarpLinearMap sw2;
+#endif
+  uint32_t lane_pow;  // x^(128*(31-lane)) [* einv]: alignment of lane l's folded partials in the tile's final fold
+  __device__ __forceinline__ void init(const CrcTables *__restrict__ t, uint32_t lane) {
+    const uint32_t *gt = &t->slice[0][0], *ga = &t->advc[0][0];
+    w.init([&](uint32_t x) { return gt[768 + (x & 0xFF)] ^ gt[512 + ((x >> 8) & 0xFF)] ^ gt[256 + ((x >> 16) & 0xFF)] ^ gt[x >> 24]; }, lane);
+    s.init([&](uint32_t x) { return ga[x & 0xFF] ^ ga[256 + ((x >> 8) & 0xFF)] ^ ga[512 + ((x >> 16) & 0xFF)] ^ ga[768 + (x >> 24)]; }, lane);
+    lane_pow = t->pow_word[4 * (31 - lane)];
+#if TEZGPU_CRC_ILP
+    const uint32_t *g2 = &t->advc2[0][0];
+    sw2.init([&](uint32_t x) { return g2[x & 0xFF] ^ g2[256 + ((x >> 8) & 0xFF)] ^ g2[512 + ((x >> 16) & 0xFF)] ^ g2[768 + (x >> 24)]; }, lane);
+    lane_pow = crc_multmodp(lane_pow, t->einv);
+#endif
+  }
+  // all 32 lanes together (lanes without a chunk pass zeros, which stay zero); last = this is the thread's last chunk
+  __device__ __forceinline__ uint32_t fold(uint32_t c, uint4 v, bool last) const {
+#if TEZGPU_CRC_ILP
+    (void)last;
+    const uint32_t u = w.apply(c ^ v.x) ^ v.y;
+    const uint32_t r = w.apply(v.z) ^ v.w;
+    return sw2.apply(u) ^ s.apply(r);
+#else
+    uint32_t x = w.apply(c ^ v.x) ^ v.y;
+    x = w.apply(x) ^ v.z;
+    x = w.apply(x) ^ v.w;
+    return last ? w.apply(x) : s.apply(x);
+#endif
   }
 };
 

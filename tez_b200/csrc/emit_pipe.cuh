@@ -94,14 +94,10 @@ __global__ void __launch_bounds__(FE_THREADS * SUBS, SUBS > 1 ? 1 : TEZGPU_EMIT4
   for (int i = threadIdx.x; i < 4 * 256; i += FE_THREADS * SUBS) s_adv128[i] = (&e.crc->adv128[0][0])[i];
   __syncthreads();
   if (tile >= ntiles) return;
-  const uint32_t lane_pow = e.crc->pow_word[4 * (31 - lane)];
-  WarpLinearMap m_word, m_skip;  // "* x^32" and "* x^(32*(4*FE_THREADS-3))" as warp-resident digit tables
-  {
-    const uint32_t *gt = &e.crc->slice[0][0], *ga = &e.crc->advc[0][0];
-    if (SUBS == 1)
-      m_word.init([&](uint32_t x) { return gt[768 + (x & 0xFF)] ^ gt[512 + ((x >> 8) & 0xFF)] ^ gt[256 + ((x >> 16) & 0xFF)] ^ gt[x >> 24]; }, lane);
-    m_skip.init([&](uint32_t x) { return ga[x & 0xFF] ^ ga[256 + ((x >> 8) & 0xFF)] ^ ga[512 + ((x >> 16) & 0xFF)] ^ ga[768 + (x >> 24)]; }, lane);
-  }
+  CrcChunkFold cf;  // the chunk fold's linear maps as warp-resident digit tables (crc32.cuh)
+  cf.init(e.crc, lane);
+  const uint32_t lane_pow = SUBS == 1 ? cf.lane_pow : e.crc->pow_word[4 * (31 - lane)];
+  const WarpLinearMap &m_word = cf.w, &m_skip = cf.s;
   const uint32_t *wt = s_wtab + lane;  // this lane's bank
   auto next_word = [&](uint32_t x) -> uint32_t {
     if (SUBS == 1) return m_word.apply(x);
@@ -275,10 +271,14 @@ __global__ void __launch_bounds__(FE_THREADS * SUBS, SUBS > 1 ? 1 : TEZGPU_EMIT4
             stg_stream_v4(gp, w);
           }
         }
-        uint32_t x = next_word(c ^ w.x) ^ w.y;
-        x = next_word(x) ^ w.z;
-        x = next_word(x) ^ w.w;
-        c = (it + 1 == iters) ? next_word(x) : m_skip.apply(x);
+        if (SUBS == 1) {
+          c = cf.fold(c, w, it + 1 == iters);
+        } else {
+          uint32_t x = next_word(c ^ w.x) ^ w.y;
+          x = next_word(x) ^ w.z;
+          x = next_word(x) ^ w.w;
+          c = (it + 1 == iters) ? next_word(x) : m_skip.apply(x);
+        }
       }
     }
     s_part[slot][tid] = c;

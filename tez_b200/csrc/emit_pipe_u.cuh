@@ -76,13 +76,9 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast
   if (tile >= ntiles) return;
   s_tab[tid] = e.crc->slice[0][tid];
   for (int i = tid; i < 4 * 256; i += FE_THREADS) s_adv128[i] = (&e.crc->adv128[0][0])[i];
-  const uint32_t lane_pow = e.crc->pow_word[4 * (31 - lane)];
-  WarpLinearMap m_word, m_skip;  // "* x^32" and "* x^(32*(4*FE_THREADS-3))" as warp-resident digit tables
-  {
-    const uint32_t *gt = &e.crc->slice[0][0], *ga = &e.crc->advc[0][0];
-    m_word.init([&](uint32_t x) { return gt[768 + (x & 0xFF)] ^ gt[512 + ((x >> 8) & 0xFF)] ^ gt[256 + ((x >> 16) & 0xFF)] ^ gt[x >> 24]; }, lane);
-    m_skip.init([&](uint32_t x) { return ga[x & 0xFF] ^ ga[256 + ((x >> 8) & 0xFF)] ^ ga[512 + ((x >> 16) & 0xFF)] ^ ga[768 + (x >> 24)]; }, lane);
-  }
+  CrcChunkFold cf;  // the chunk fold's linear maps as warp-resident digit tables (crc32.cuh)
+  cf.init(e.crc, lane);
+  const uint32_t lane_pow = cf.lane_pow;
   const uint32_t img_base = (uint32_t)__cvta_generic_to_shared(s_img);
   const uint8_t *__restrict__ kv = e.rec.kv;
   const uint8_t *kv_end = kv + e.rec.kv_bytes;
@@ -259,10 +255,7 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast
             stg_stream_v4(gp, w);
           }
         }
-        uint32_t x = m_word.apply(c ^ w.x) ^ w.y;
-        x = m_word.apply(x) ^ w.z;
-        x = m_word.apply(x) ^ w.w;
-        c = (it + 1 == iters) ? m_word.apply(x) : m_skip.apply(x);
+        c = cf.fold(c, w, it + 1 == iters);
       }
     }
     s_part[slot][tid] = c;

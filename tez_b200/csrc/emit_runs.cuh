@@ -206,13 +206,9 @@ __global__ void __launch_bounds__(ER_THREADS, TEZGPU_EMIT_RUNS_MIN_CTAS) k_emit_
   // ================================================================== consumers (256 threads)
   const int tid = threadIdx.x - 32 * ER_PW, cwarp = tid >> 5;
   const uint32_t magic = (uint32_t)((1ull << 32) / rec_size) + 1u;
-  const uint32_t lane_pow = e.crc->pow_word[4 * (31 - lane)];
-  WarpLinearMap m_word, m_skip;
-  {
-    const uint32_t *gt = &e.crc->slice[0][0], *ga = &e.crc->advc[0][0];
-    m_word.init([&](uint32_t x) { return gt[768 + (x & 0xFF)] ^ gt[512 + ((x >> 8) & 0xFF)] ^ gt[256 + ((x >> 16) & 0xFF)] ^ gt[x >> 24]; }, lane);
-    m_skip.init([&](uint32_t x) { return ga[x & 0xFF] ^ ga[256 + ((x >> 8) & 0xFF)] ^ ga[512 + ((x >> 16) & 0xFF)] ^ ga[768 + (x >> 24)]; }, lane);
-  }
+  CrcChunkFold cf;  // the chunk fold's linear maps as warp-resident digit tables (crc32.cuh)
+  cf.init(e.crc, lane);
+  const uint32_t lane_pow = cf.lane_pow;
   auto consumer_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(FE_THREADS) : "memory"); };
   const DevSmem sm;
 
@@ -270,10 +266,7 @@ __global__ void __launch_bounds__(ER_THREADS, TEZGPU_EMIT_RUNS_MIN_CTAS) k_emit_
             stg_stream_v4(gp, w);
           }
         }
-        uint32_t x = m_word.apply(c ^ w.x) ^ w.y;
-        x = m_word.apply(x) ^ w.z;
-        x = m_word.apply(x) ^ w.w;
-        c = (itc + 1 == iters) ? m_word.apply(x) : m_skip.apply(x);
+        c = cf.fold(c, w, itc + 1 == iters);
       }
     }
     const uint32_t row = (batch & 1u) * ER_BATCH + slot;

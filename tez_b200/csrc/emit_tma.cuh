@@ -270,13 +270,9 @@ __global__ void __launch_bounds__(ET_THREADS, TEZGPU_EMIT_TMA_MIN_CTAS) k_emit_t
     for (uint32_t b = 0; b < e.fixed_hdr_len; b++) hw[b >> 2] |= (uint32_t)e.fixed_hdr[b] << (8u * (b & 3u));
     kc.hdr = make_uint4(hw[0], hw[1], hw[2], hw[3]);
   }
-  const uint32_t lane_pow = e.crc->pow_word[4 * (31 - lane)];
-  WarpLinearMap m_word, m_skip;  // "* x^32" and "* x^(32*(4*FE_THREADS-3))" as warp-resident digit tables
-  {
-    const uint32_t *gt = &e.crc->slice[0][0], *ga = &e.crc->advc[0][0];
-    m_word.init([&](uint32_t x) { return gt[768 + (x & 0xFF)] ^ gt[512 + ((x >> 8) & 0xFF)] ^ gt[256 + ((x >> 16) & 0xFF)] ^ gt[x >> 24]; }, lane);
-    m_skip.init([&](uint32_t x) { return ga[x & 0xFF] ^ ga[256 + ((x >> 8) & 0xFF)] ^ ga[512 + ((x >> 16) & 0xFF)] ^ ga[768 + (x >> 24)]; }, lane);
-  }
+  CrcChunkFold cf;  // the chunk fold's linear maps as warp-resident digit tables (crc32.cuh)
+  cf.init(e.crc, lane);
+  const uint32_t lane_pow = cf.lane_pow;
   auto consumer_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(FE_THREADS) : "memory"); };
 
   uint32_t it = 0, slot = 0, batch = 0;
@@ -334,10 +330,7 @@ __global__ void __launch_bounds__(ET_THREADS, TEZGPU_EMIT_TMA_MIN_CTAS) k_emit_t
             stg_stream_v4(gp, w);
           }
         }
-        uint32_t x = m_word.apply(c ^ w.x) ^ w.y;
-        x = m_word.apply(x) ^ w.z;
-        x = m_word.apply(x) ^ w.w;
-        c = (itc + 1 == iters) ? m_word.apply(x) : m_skip.apply(x);
+        c = cf.fold(c, w, itc + 1 == iters);
       }
     }
     const uint32_t row = (batch & 1u) * ET_BATCH + slot;

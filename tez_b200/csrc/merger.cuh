@@ -36,12 +36,8 @@ __global__ void __launch_bounds__(CRCV_THREADS)
   s_tab[tid] = t->slice[0][tid];
   for (int i = tid; i < 4 * 256; i += CRCV_THREADS) s_adv128[i] = (&t->adv128[0][0])[i];
   // the two maps of the 16-byte-chunk interleave as warp-resident digit tables (crc32.cuh)
-  WarpLinearMap m_word, m_skip;
-  {
-    const uint32_t *gt = &t->slice[0][0], *ga = &t->advc[0][0];
-    m_word.init([&](uint32_t x) { return gt[768 + (x & 0xFF)] ^ gt[512 + ((x >> 8) & 0xFF)] ^ gt[256 + ((x >> 16) & 0xFF)] ^ gt[x >> 24]; }, lane);
-    m_skip.init([&](uint32_t x) { return ga[x & 0xFF] ^ ga[256 + ((x >> 8) & 0xFF)] ^ ga[512 + ((x >> 16) & 0xFF)] ^ ga[768 + (x >> 24)]; }, lane);
-  }
+  CrcChunkFold cf;
+  cf.init(t, lane);
   const uint32_t piece = blockIdx.x;
   uint32_t lo = 0, hi = nseg;  // last segment with piece_start[s] <= piece
   while (hi - lo > 1) {
@@ -80,10 +76,7 @@ __global__ void __launch_bounds__(CRCV_THREADS)
           v = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
-      uint32_t x = m_word.apply(c ^ v.x) ^ v.y;
-      x = m_word.apply(x) ^ v.z;
-      x = m_word.apply(x) ^ v.w;
-      c = (it + 1 == iters) ? m_word.apply(x) : m_skip.apply(x);
+      c = cf.fold(c, v, it + 1 == iters);
     }
   }
   s_part[tid] = c;
@@ -96,7 +89,7 @@ __global__ void __launch_bounds__(CRCV_THREADS)
       q = s_adv128[q & 0xFF] ^ s_adv128[256 + ((q >> 8) & 0xFF)] ^ s_adv128[512 + ((q >> 16) & 0xFF)] ^ s_adv128[768 + (q >> 24)];
       q ^= s_part[lane + 32 * k];
     }
-    q = crc_multmodp(q, t->pow_word[4 * (31 - lane)]);
+    q = crc_multmodp(q, cf.lane_pow);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q ^= __shfl_xor_sync(0xffffffffu, q, o);
     if (lane == 0) {
@@ -573,6 +566,8 @@ class Merger {
       check_verdicts();
       if (!mismatch) {
         parsed_fixed = true;
+        parse_mode = 0;
+        parse_rounds = 0;
         launches += pipe.state.launches;
         cursor = 0;
         have_kvoff = false;
@@ -660,6 +655,7 @@ class Merger {
   // point.  Returns false when the rounds cap is hit (adversarial bytes): the caller falls back to the sequential walker.
   DeviceBuffer d_pwseg, d_entry[2], d_wcount, d_wbase, d_wlast, d_carry, d_pwflags;
   int parse_rounds = 0;
+  int parse_mode = 0;   // how the last open() found the records: 0 fixed framing (run table), 1 window parser, 2 sequential walker
   bool parse_parallel(uint32_t nseg) {
     cudaStream_t st = pipe.stream;
     std::vector<PwSeg> ps(nseg);
@@ -701,9 +697,9 @@ class Merger {
       parse_rounds++;
       cur ^= 1;
     }
-    if (flags[0]) return false;
+    // not converged, or converged on a walk that died (malformed record / early EOF): the sequential walker decides
+    if (flags[0] || flags[1]) return false;
     cur ^= 1;  // the entries the last (unchanged) round walked from
-    TG_CHECK(flags[1] == 0, TEZGPU_E_FORMAT, "malformed IFile segment " + std::to_string(flags[1] ? seg_orig[flags[1] - 1] : 0));
     // ---- record offsets of every window, totals
     const uint32_t nblk = (uint32_t)div_up(nwin, SCAN_TILE);
     pipe.blk.ensure(((size_t)nblk + 2) * 8);
@@ -747,7 +743,9 @@ class Merger {
   void open_general_reparse(uint32_t nseg, std::vector<uint64_t> &counts, std::vector<uint64_t> &rec_base) {
     cudaStream_t st = pipe.stream;
     static const bool serial_only = getenv("TEZGPU_PARSE_SERIAL") && atoi(getenv("TEZGPU_PARSE_SERIAL")) != 0;
+    parse_mode = 1;
     if (!serial_only && parse_parallel(nseg)) return;
+    parse_mode = 2;
     int *d_bad = pipe.d_error();
     ParseArrays pa{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     k_parse_segments<false><<<(uint32_t)div_up(nseg, PARSE_WARPS), PARSE_WARPS * 32, 0, st>>>(data, d_segs.as<SegDesc>(), nseg, d_counts.as<uint64_t>(),

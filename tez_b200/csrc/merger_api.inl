@@ -41,6 +41,14 @@ int32_t tezgpu_merge_set_check_for_same_keys(tezgpu_merger *m, int32_t check_for
   TG_API_END
 }
 
+int32_t tezgpu_merge_parse_info(tezgpu_merger *m, int32_t *mode, int32_t *rounds) {
+  TG_API_BEGIN
+  TG_CHECK(m, TEZGPU_E_INVALID, "null handle");
+  if (mode) *mode = m->m.parse_mode;
+  if (rounds) *rounds = m->m.parse_rounds;
+  TG_API_END
+}
+
 int32_t tezgpu_merge_counts(tezgpu_merger *m, uint64_t *records, uint64_t *kv_bytes) {
   TG_API_BEGIN
   TG_CHECK(m, TEZGPU_E_INVALID, "null handle");

@@ -29,7 +29,7 @@ namespace tezgpu {
 struct SegDesc;  // merger.cuh
 
 constexpr uint32_t PW_WINDOW = 32768;
-constexpr uint32_t PW_MAX_TRIES = 2048;   // candidate start offsets per window in the guess round
+constexpr uint32_t PW_MAX_TRIES = 8192;   // candidate start offsets per window in the guess round (covers records up to 8 KiB)
 constexpr int PW_THREADS = 128;
 constexpr uint64_t PW_EOF = ~0ull;        // the reader met the EOF markers before this window
 constexpr uint64_t PW_BAD = ~0ull - 1;    // the walk that produced this entry met a malformed record
@@ -116,6 +116,7 @@ struct PwWalk {
   uint32_t n;           // records that start in the window
   uint64_t lk_off, lk_len;  // last full key seen (segment offset, length); lk_off = ~0 when none
   uint64_t bytes;       // EMIT: key + value bytes
+  bool early_eof;       // the EOF markers were met before the last two bytes of the body
 };
 
 // the sequential reader over one window, from entry e
@@ -128,6 +129,7 @@ __device__ __forceinline__ PwWalk pw_walk(const uint8_t *__restrict__ seg, const
   r.lk_off = ~0ull;
   r.lk_len = 0;
   r.bytes = 0;
+  r.early_eof = false;
   if (e == PW_EOF || e == PW_BAD) return r;
   uint64_t pos = e >> 1;
   int state = (int)(e & 1u);        // 1: the previous record was a repeat (cur_klen == -2 in the walker of merger.cuh)
@@ -150,7 +152,7 @@ __device__ __forceinline__ PwWalk pw_walk(const uint8_t *__restrict__ seg, const
       if (ok) ok = pw_vlong(seg, sd.len, p2, sd.body_end, vl);
     }
     if (!ok) { status = 2; break; }
-    if (kl == -1 && vl == -1) { status = 1; break; }                   // EOF markers
+    if (kl == -1 && vl == -1) { status = 1; r.early_eof = p2 != sd.body_end; break; }   // EOF markers
     if ((kl != -2 && kl < 0) || vl < 0 || kl > 0x7fffffffll || vl > 0x7fffffffll) { status = 2; break; }
     uint64_t q = p2;
     if (kl != -2) {
@@ -183,11 +185,30 @@ __device__ __forceinline__ PwWalk pw_walk(const uint8_t *__restrict__ seg, const
   return r;
 }
 
+// the exit of the first candidate start (offset, reader state) in window [ws, wend) whose walk survives to the window's
+// end (EOF markers count only where a well-formed body has them: in its last two bytes); PW_BAD when none does
+__device__ __noinline__ uint64_t pw_guess(const uint8_t *__restrict__ seg, const PwSeg &sd, uint32_t s, uint64_t ws, uint64_t wend,
+                                          bool last_win, const PwArrays &out) {
+  for (uint32_t o = 0; o < PW_MAX_TRIES && ws + o < wend; o++)
+    for (uint64_t st = 0; st < 2; st++) {
+      const PwWalk r = pw_walk<false>(seg, sd, s, wend, last_win, ((ws + o) << 1) | st, 0, ~0ull, 0, out);
+      if (r.exit_v != PW_BAD && !r.early_eof) return r.exit_v;
+    }
+  return PW_BAD;
+}
+
 // One thread per window.
-//   MODE 0  guess round: first windows walk from the body start, every other window from the first candidate start
-//           (offset, reader state) whose walk survives to the window's end; publishes the exit as the next entry.
+//   MODE 0  guess round: first windows walk from the body start, every other window publishes pw_guess as the next
+//           window's entry.
 //   MODE 1  counting round: walks from entry_in, publishes the exit, sets flags[0] when it differs from the entry the
-//           next window used, records the window's record count and its last full key.
+//           next window used, records the window's record count and its last full key.  A walk that DIES (malformed
+//           record, EOF markers before the body's end, or an entry that is itself the trace of a dead walk) was started
+//           from a wrong entry -- or the data is malformed: it publishes pw_guess instead of its death (a dead exit
+//           would travel on, one window per round, long after the wrong entry that caused it was corrected) and raises
+//           flags[1].  A round with flags[0] == 0 and flags[1] == 0 walked every window from its true entry (induction
+//           from the first window) and met no malformed record: its counts are the sequential reader's.  flags[1] in
+//           a round that changed nothing means malformed input (or an early EOF): the caller takes the sequential
+//           walker, which reports it the way IFile.Reader does.
 //   MODE 2  emitting round: entries are final; writes the per-record metadata at rec_base[w]...
 template <int MODE>
 __global__ void __launch_bounds__(PW_THREADS)
@@ -209,10 +230,7 @@ __global__ void __launch_bounds__(PW_THREADS)
     const bool last_win = (k + 1 == sd.nwin);
     PwWalk r;
     if (MODE == 0 && k > 0) {
-      r.exit_v = PW_BAD;
-      for (uint32_t o = 0; o < PW_MAX_TRIES && ws + o < wend && r.exit_v == PW_BAD; o++)
-        for (uint64_t st = 0; st < 2 && r.exit_v == PW_BAD; st++)
-          r = pw_walk<false>(seg, sd, s, wend, last_win, ((ws + o) << 1) | st, 0, ~0ull, 0, out);
+      r.exit_v = last_win ? PW_EOF : pw_guess(seg, sd, s, ws, wend, last_win, out);
     } else {
       const uint64_t e = (k == 0) ? (sd.body0 << 1) : entry_in[w];
       r = pw_walk<EMIT>(seg, sd, s, wend, last_win, e, EMIT ? rec_base[w] : 0, EMIT ? carry[2 * (uint64_t)w] : ~0ull,
@@ -225,16 +243,16 @@ __global__ void __launch_bounds__(PW_THREADS)
       wcount[w] = r.n;
       wlastkey[2 * (uint64_t)w] = r.lk_off;
       wlastkey[2 * (uint64_t)w + 1] = r.lk_len;
+      const uint64_t e_in = (k == 0) ? (sd.body0 << 1) : entry_in[w];
+      // the stream must end with the EOF markers, in the last window, and nowhere else
+      const bool died = r.exit_v == PW_BAD || e_in == PW_EOF || r.early_eof || (last_win ? r.exit_v != PW_EOF : r.exit_v == PW_EOF);
+      if (died) atomicMax(flags + 1, (int)s + 1);
       if (!last_win) {
-        if (entry_in[w + 1] != r.exit_v) flags[0] = 1;
-        entry_out[w + 1] = r.exit_v;
-      } else if (r.exit_v != PW_EOF) {
-        // the stream must end with the EOF markers (only meaningful in the round that changed nothing: the host reads
-        // flags[1] from that round alone)
-        atomicMax(flags + 1, (int)s + 1);
+        const uint64_t x = (died && k > 0) ? pw_guess(seg, sd, s, ws, wend, last_win, out) : r.exit_v;
+        if (entry_in[w + 1] != x) flags[0] = 1;
+        entry_out[w + 1] = x;
       }
       if (k == 0) entry_out[w] = sd.body0 << 1;
-      if (r.exit_v == PW_BAD) atomicMax(flags + 1, (int)s + 1);
     } else {
       if (r.exit_v == PW_BAD) atomicMax(flags + 1, (int)s + 1);
       my_bytes = r.bytes;

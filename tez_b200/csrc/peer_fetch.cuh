@@ -107,13 +107,9 @@ __global__ void __launch_bounds__(FV_THREADS)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   s_tab[tid] = t->slice[0][tid];
   for (int i = tid; i < 4 * 256; i += FV_THREADS) s_adv128[i] = (&t->adv128[0][0])[i];
-  WarpLinearMap m_word, m_skip;
-  {
-    const uint32_t *gt = &t->slice[0][0], *ga = &t->advc[0][0];
-    m_word.init([&](uint32_t x) { return gt[768 + (x & 0xFF)] ^ gt[512 + ((x >> 8) & 0xFF)] ^ gt[256 + ((x >> 16) & 0xFF)] ^ gt[x >> 24]; }, lane);
-    m_skip.init([&](uint32_t x) { return ga[x & 0xFF] ^ ga[256 + ((x >> 8) & 0xFF)] ^ ga[512 + ((x >> 16) & 0xFF)] ^ ga[768 + (x >> 24)]; }, lane);
-  }
-  const uint32_t lane_pow = t->pow_word[4 * (31 - lane)];
+  CrcChunkFold cf;
+  cf.init(t, lane);
+  const uint32_t lane_pow = cf.lane_pow;
   __syncthreads();
   for (uint32_t piece = blockIdx.x; piece < npieces; piece += gridDim.x) {
     uint32_t lo = 0, hi = nseg;  // last segment with piece_start[s] <= piece
@@ -176,10 +172,7 @@ __global__ void __launch_bounds__(FV_THREADS)
               w = make_uint4(ww[0], ww[1], ww[2], ww[3]);
             }
           }
-          uint32_t x = m_word.apply(c ^ w.x) ^ w.y;
-          x = m_word.apply(x) ^ w.z;
-          x = m_word.apply(x) ^ w.w;
-          c = (it0 + u + 1 == iters) ? m_word.apply(x) : m_skip.apply(x);
+          c = cf.fold(c, w, it0 + u + 1 == iters);
         }
         i += (int32_t)(FV_UNROLL * FV_THREADS);
       }

@@ -589,6 +589,52 @@ uint32_t tezgpu_debug_assemble_emulate(const uint8_t *stage, uint32_t nr, uint32
   return body_end;
 }
 
+// Host emulation of the chunk-interleaved checksum of the emit / verify kernels (crc32.cuh CrcChunkFold): 256 threads,
+// thread t folds chunks i = Cn + t - iters*256 (+256 ...), partials are combined by the adv128 second-level fold, the
+// per-lane alignment multiplier and an xor across lanes.  ilp = 1 runs the two-deep fold with the einv correction,
+// ilp = 0 the textbook chain.  Returns the raw remainder (init 0, no final xor) of the nchunks * 16 bytes.
+uint32_t tezgpu_debug_chunk_fold_emulate(const uint8_t *data, uint32_t nchunks, int32_t ilp) {
+  CrcTables *t = new CrcTables();
+  const int T = EMIT_CRC_STRIDE_WORDS;
+  crc_build_tables(*t, T);
+  auto tab = [](const uint32_t(*m)[256], uint32_t x) { return m[0][x & 0xFF] ^ m[1][(x >> 8) & 0xFF] ^ m[2][(x >> 16) & 0xFF] ^ m[3][x >> 24]; };
+  auto W = [&](uint32_t x) { return t->slice[3][x & 0xFF] ^ t->slice[2][(x >> 8) & 0xFF] ^ t->slice[1][(x >> 16) & 0xFF] ^ t->slice[0][x >> 24]; };
+  auto S = [&](uint32_t x) { return tab(t->advc, x); };
+  auto SW2 = [&](uint32_t x) { return tab(t->advc2, x); };
+  const uint32_t Cn = nchunks, iters = (Cn + T - 1) / T;
+  std::vector<uint32_t> part(T, 0);
+  for (int tid = 0; tid < T; tid++) {
+    int64_t i = (int64_t)Cn + tid - (int64_t)iters * T;
+    uint32_t c = 0;
+    for (uint32_t it = 0; it < iters; it++, i += T) {
+      uint32_t w[4] = {0, 0, 0, 0};
+      if (i >= 0) memcpy(w, data + 16 * i, 16);
+      if (ilp) {
+        const uint32_t u = W(c ^ w[0]) ^ w[1], r = W(w[2]) ^ w[3];
+        c = SW2(u) ^ S(r);
+      } else {
+        uint32_t x = W(c ^ w[0]) ^ w[1];
+        x = W(x) ^ w[2];
+        x = W(x) ^ w[3];
+        c = (it + 1 == iters) ? W(x) : S(x);
+      }
+    }
+    part[tid] = c;
+  }
+  uint32_t total = 0;
+  for (int lane = 0; lane < 32; lane++) {
+    uint32_t q = 0;
+    for (int kk = 0; kk < T / 32; kk++) q = tab(t->adv128, q) ^ part[lane + 32 * kk];
+    uint32_t lp = t->pow_word[4 * (31 - lane)];
+    if (ilp) lp = crc_multmodp(lp, t->einv);
+    total ^= crc_multmodp(q, lp);
+  }
+  // the identity the correction rests on: einv * x^(128*(T-1)) == 1
+  if (crc_multmodp(t->einv, crc_host_xpow8((uint64_t)16 * (uint64_t)(T - 1))) != 0x80000000u) total = ~total;
+  delete t;
+  return total;
+}
+
 // Host emulation of the run-range emit kernel's chunk assembly (emit_runs.cuh): record j of the tile is the rec_size
 // bytes at staging[src[j]...]; builds the output image chunk by chunk with the kernel's template code.
 uint32_t tezgpu_debug_runs_assemble_emulate(const uint8_t *staging, uint32_t staging_len, const uint32_t *src, uint32_t nr,

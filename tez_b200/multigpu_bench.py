@@ -11,11 +11,6 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-KEY_LEN, VAL_LEN = 16, 64
-REC = KEY_LEN + VAL_LEN
-OUT_REC = REC + 2
-
-
 def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores, verify_partition=None):
     """verify_partition(run_bytes_list, merged_segment_bytes) -> None or raises: the caller's checker (bench.py passes the
     CPU oracle's TezMerger restatement); run on every rank for one owned partition AFTER the timed region."""
@@ -31,8 +26,19 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores, veri
     os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
     os.environ.setdefault("NCCL_NCHANNELS_PER_PEER", "32")
     dist.init_process_group("nccl", device_id=dev)
-    n, P = args.records, 1024
-    d_kv = synth.gen_c2(rank * n, n, seed=4, device=dev)
+    config = getattr(args, "config", 4)
+    if config == 5:
+        # BASELINE config 5: Zipf(1.1) keys, 4 KB values, 256 partitions -- partition imbalance, run-length encoded
+        # segments (the producers' AUTO rule turns RLE on), general parse / merge / emit on the reduce side
+        KEY_LEN, VAL_LEN, P = 16, 4096, 256
+        REC, OUT_REC = KEY_LEN + VAL_LEN, KEY_LEN + VAL_LEN + 4      # vint(16) = 1 byte, vint(4096) = 3 bytes
+        n = args.records
+        d_kv = synth.gen_c5(rank * n, n, seed=5, val_len=VAL_LEN, device=dev)
+    else:
+        KEY_LEN, VAL_LEN, P = 16, 64, 1024
+        REC, OUT_REC = KEY_LEN + VAL_LEN, KEY_LEN + VAL_LEN + 2
+        n = args.records
+        d_kv = synth.gen_c2(rank * n, n, seed=4, device=dev)
     torch.cuda.synchronize()   # the library works on its own stream
     sorter = T.GpuSorter(P, fixed=(KEY_LEN, VAL_LEN), device=local)
     cap = n * OUT_REC + 10 * P + 4096
@@ -196,6 +202,11 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores, veri
             verify_partition(runs, merged)
             checked[0] = 1
     dist.all_reduce(checked)
+    # partition imbalance: merged bytes this rank ends up owning (max / mean over the ranks)
+    own = torch.tensor([float(last_step[2])], device=dev, dtype=torch.float64)
+    own_max, own_sum = own.clone(), own.clone()
+    dist.all_reduce(own_max, op=dist.ReduceOp.MAX)
+    dist.all_reduce(own_sum)
     if rank == 0:
         total_records = n * world
         assert int(tot[0].item()) == total_records, "records lost in the shuffle"
@@ -203,10 +214,10 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores, veri
         peak, peak_src = hbm_peak()
         avg = {k: round(sum(v) / len(v), 3) for k, v in phase_ms.items()}
         sent = int(n * OUT_REC * (world - 1) / world)
-        line = {"metric": "sorted KV GB/s (16B key / 64B val)", "value": round(value, 3), "unit": "GB/s",
+        line = {"metric": "sorted KV GB/s (16B key / %dB val)" % VAL_LEN, "value": round(value, 3), "unit": "GB/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 4),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": workload_config(world, n), "clocks": clk, "gpu_launches": int(tot[1].item()),
+                "config": workload_config(world, n, config) if config == 5 else workload_config(world, n), "clocks": clk, "gpu_launches": int(tot[1].item()),
                 "e2e": None,
                 "phases_ms_rank0": avg,
                 "phases_ms_over_ranks": {k: [round(float(ph_min[i]), 3), round(float(ph_max[i]), 3)]
@@ -218,10 +229,13 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores, veri
                            "transport": transport + (" + sort(k+1) overlapped with pull(k)" if overlap else ""), "reference_GBps": 770,
                            "note": ("peer pull: index all-gather (NCCL) + one fetch kernel over CUDA IPC mappings; own partitions merged in place"
                                     if px else "variable-size all-to-all (NCCL send/recv) incl. index all-gather")},
-                "roofline": {"bound": "hbm", "achieved": round(n * (2 * 162) / (ms_step * 1e-3) / 1e9, 1), "peak": peak,
-                             "unit": "GB/s", "frac": round(n * (2 * 162) / (ms_step * 1e-3) / 1e9 / peak, 4),
+                "roofline": {"bound": "hbm", "achieved": round(n * (2 * (REC + OUT_REC)) / (ms_step * 1e-3) / 1e9, 1), "peak": peak,
+                             "unit": "GB/s", "frac": round(n * (2 * (REC + OUT_REC)) / (ms_step * 1e-3) / 1e9 / peak, 4),
                              "traffic": None, "peak_source": peak_src,
-                             "note": "per GPU: sort (162 B/rec) + merge (164 B/rec) algorithmic bytes over the whole step"},
+                             "note": "per GPU: sort (read key+value, write framed record) + merge (read + write the framed "
+                                     "records) algorithmic bytes over the whole step, without run-length savings"},
+                "imbalance": {"max_owned_bytes": int(own_max.item()), "mean_owned_bytes": int(own_sum.item() / world),
+                              "max_over_mean": round(float(own_max.item()) / max(1.0, own_sum.item() / world), 3)},
                 "parity_check": {"ranks_checked": int(checked.item()),
                                  "what": "after the timed region every rank compared one owned partition's merged segment with the CPU "
                                          "oracle's TezMerger over the G runs it merged (byte-exact) and its CRC32 trailer with zlib"},

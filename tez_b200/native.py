@@ -178,6 +178,12 @@ class GpuMerger:
         """MergeQueue's checkForSameKeys (SORT/TezMerger.java:560-573); default True."""
         check(self.L.tezgpu_merge_set_check_for_same_keys(self.h, 1 if on else 0))
 
+    def parse_info(self):
+        """(mode, rounds) of the last open: 0 records addressed in place, 1 window parser, 2 sequential walker."""
+        m, r = C.c_int32(), C.c_int32()
+        check(self.L.tezgpu_merge_parse_info(self.h, C.byref(m), C.byref(r)))
+        return m.value, r.value
+
     def counts(self):
         r, b = C.c_uint64(), C.c_uint64()
         check(self.L.tezgpu_merge_counts(self.h, C.byref(r), C.byref(b)))

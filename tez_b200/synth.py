@@ -57,3 +57,36 @@ def hash_bytes(keys):
 
 def hash_partition(keys, num_partitions):
     return (hash_bytes(keys) & 0x7FFFFFFF) % num_partitions
+
+
+def zipf_ids(first_index, n, seed=5, s=1.1, num_ids=1 << 32, device="cpu"):
+    """Record i -> an id in [0, num_ids) drawn Zipf(s) by inversion of the continuous approximation of the CDF
+    (rank = (1 - u * (1 - N^(1-s)))^(1/(1-s)), u = splitmix64 counter in [0, 1)); int64 tensor.  Deterministic per device
+    type; tests download the records they generated instead of re-deriving them on the host."""
+    i = torch.arange(first_index, first_index + n, device=device, dtype=torch.int64)
+    sbits = (seed << 56)
+    if sbits >= 1 << 63:
+        sbits -= 1 << 64
+    u = (_lsr(splitmix64(i ^ sbits), 11)).to(torch.float64) * (1.0 / 9007199254740992.0)
+    a = 1.0 - s
+    rank = torch.pow(1.0 - u * (1.0 - float(num_ids) ** a), 1.0 / a)
+    return torch.clamp(rank.to(torch.int64) - 1, 0, num_ids - 1)
+
+
+def gen_c5(first_index, n, seed=5, val_len=4096, device="cpu", chunk=1 << 16):
+    """BASELINE config 5 records: key = 16 bytes rendered from a Zipf(1.1) id over 2^32 ids (two big-endian
+    splitmix64 words of the id, so equal ids <=> equal keys and keys are spread over the partitions), value = val_len
+    bytes, a pure function of the key.  Returns a uint8 tensor of n * (16 + val_len) bytes."""
+    assert val_len % 8 == 0
+    rec = 16 + val_len
+    out = torch.empty(n * rec, dtype=torch.uint8, device=device)
+    vw = torch.arange(val_len // 8, device=out.device, dtype=torch.int64)
+    for s0 in range(0, n, chunk):
+        m = min(chunk, n - s0)
+        ids = zipf_ids(first_index + s0, m, seed=seed, device=out.device)
+        k = torch.stack([splitmix64(ids * 2 + 0x1234567), splitmix64(ids * 2 + 0x7654321)], dim=1)
+        v = splitmix64((ids.unsqueeze(1) << 10) ^ vw ^ 0x5A5A5A5A)
+        view = out[s0 * rec:(s0 + m) * rec].view(m, rec)
+        view[:, :16] = _be_bytes(k)
+        view[:, 16:] = _be_bytes(v)
+    return out
