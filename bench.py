@@ -164,6 +164,20 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def single_sorter_cpu(records, partitions, threads, repeats=3):
+    """The config-2 shape itself on the host: ONE PipelinedSorter over `records` records (spans of 2^20 records sorted
+    by `threads` sort threads, SpanMerger heap over the spans, one IFile writer), `repeats` runs -> GB/s of each."""
+    from oracle import tez_oracle as O
+    from tez_b200 import synth
+    kv = synth.gen_c2(0, records, seed=2, device="cpu").numpy()
+    conf = O.sorter_conf(partitions, sort_threads=threads)
+    out = []
+    for _ in range(repeats):
+        secs, _ = O.bench_pipelined_fixed(conf, kv, KEY_LEN, VAL_LEN, 1)
+        out.append(round(records * REC / secs / 1e9, 4))
+    return out
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -172,7 +186,15 @@ def reference_arm(args):
     per_task = args.cpu_records_per_task
     partitions = 64 if args.gpus == 1 else 1024
     value, secs, n = run_cpu(cores, per_task, args.steps, args.warmup, partitions)
-    sample = "%d records (%d per task x %d tasks, one PipelinedSorter task per core)" % (n, per_task, cores)
+    sample = "%d records (%d per task x %d tasks, one PipelinedSorter task per core, %d spans + SpanMerger each)" % (
+        n, per_task, cores, (per_task + (1 << 20) - 1) >> 20)
+    single = None
+    if args.cpu_single_records > 0:
+        # one sorter, as BASELINE.md describes config 2, on a bounded sample: tez.runtime.pipelined.sorter.sort.threads
+        # = 2 (the default) and = cores; three repeats each (the spread is the honest error bar of this arm)
+        single = {"records": args.cpu_single_records,
+                  "sort_threads_2_gbs": single_sorter_cpu(args.cpu_single_records, partitions, 2),
+                  "sort_threads_%d_gbs" % cores: single_sorter_cpu(args.cpu_single_records, partitions, cores)}
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(secs * 1e3, 3), "higher_is_better": True,
@@ -180,8 +202,12 @@ def reference_arm(args):
         "config": workload_config(args.gpus, args.records),
         "cpu_baseline": {"value": round(value, 4), "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "CPU restatement of PipelinedSorter (oracle/tez_oracle.c), not the JVM: no JDK / Hadoop jars exist in this image",
+        "note": "CPU restatement of PipelinedSorter (oracle/tez_oracle.c), not the JVM: no JDK / Hadoop jars exist in this image; "
+                "value = all host cores busy with independent sorter tasks (the most favourable use of the box for the CPU); "
+                "single_sorter = ONE sorter over a bounded sample of config 2 at sort.threads 2 and = cores, three repeats",
     }
+    if single:
+        line["cpu_baseline"]["single_sorter"] = single
     print(json.dumps(line))
     return 0
 
@@ -499,7 +525,10 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--records", type=int, default=None,
                     help="records per GPU (default: 1e8 at N=1 = BASELINE config 2; 1.25e8 at N>1 = config 4's 1e9 over 8 GPUs)")
-    ap.add_argument("--cpu-records-per-task", type=int, default=1_000_000)
+    ap.add_argument("--cpu-records-per-task", type=int, default=1_500_000,
+                    help="CPU arm: records per PipelinedSorter task (> 2^20 so that every task has two spans and its SpanMerger runs)")
+    ap.add_argument("--cpu-single-records", type=int, default=10_000_000,
+                    help="reference arm: records of the single-sorter sample (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-g1-pipeline", action="store_true")

@@ -1052,13 +1052,14 @@ typedef struct {
   uint32_t klen, vlen;
   uint64_t n;
   uint64_t out_bytes;
+  int sort_threads;
 } bench_task;
 
 static void *bench_worker(void *arg) {
   bench_task *t = (bench_task *)arg;
   tzo_sorter_result r;
   tzo_sorter_conf c = *t->conf;
-  c.sort_threads = 1;
+  c.sort_threads = t->sort_threads;
   tzo_pipelined_sort_fixed(&c, t->kv, t->klen, t->vlen, t->n, &r);
   t->out_bytes = r.file_out.len;
   tzo_sorter_result_free(&r);
@@ -1077,6 +1078,8 @@ double tzo_bench_pipelined_fixed(const tzo_sorter_conf *conf, const uint8_t *kv,
     bt[t].conf = conf;
     bt[t].kv = kv + (uint64_t)t * per * (klen + vlen);
     bt[t].klen = klen; bt[t].vlen = vlen;
+    /* one task: the sorter's own span-sort pool (conf->sort_threads); many concurrent tasks: one sort thread each */
+    bt[t].sort_threads = tasks == 1 ? (conf->sort_threads > 0 ? conf->sort_threads : 1) : 1;
     bt[t].n = (t == tasks - 1) ? n - per * (uint64_t)(tasks - 1) : per;
     pthread_create(&th[t], NULL, bench_worker, &bt[t]);
   }
