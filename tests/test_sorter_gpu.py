@@ -96,6 +96,50 @@ def test_c4_shape_1024_partitions_bit_exact(n):
     assert st["output_records"] == n and not st["rle_used"]
 
 
+def test_look_back_kernels_make_progress_next_to_other_streams():
+    """The chained-scan kernels (radix_sort.cuh, k_part_bounds) wait on the tile before them and identify tiles by
+    blockIdx: forward progress relies on CTAs of ONE grid being dispatched in index order, also when another stream's
+    kernels occupy SMs (the multi-GPU step runs the peer pull next to the sort).  Two competing streams keep every SM
+    busy with long kernels while sorts of several sizes run; every result must still equal the oracle's."""
+    import threading
+    import torch
+    n = 3_000_000
+    kv = O.gen_c2(0, n, seed=21)
+    exp = O.pipelined_sort_fixed(O.sorter_conf(64), kv, 16, 64)
+    stop = threading.Event()
+
+    def hog():
+        torch.cuda.set_device(0)
+        st = torch.cuda.Stream()
+        a = torch.randn(4096, 4096, device="cuda")
+        junk = torch.empty(1 << 28, dtype=torch.uint8, device="cuda")
+        with torch.cuda.stream(st):
+            while not stop.is_set():
+                for _ in range(4):
+                    a = torch.tanh(a @ a * 1e-3)      # full-grid GEMMs + elementwise kernels
+                    junk.add_(1)                      # bandwidth-bound grid of > 1e5 CTAs
+                st.synchronize()
+
+    threads = [threading.Thread(target=hog) for _ in range(2)]
+    for t in threads:
+        t.start()
+    try:
+        with T.GpuSorter(64, fixed=(16, 64)) as s:
+            d_kv = torch.from_numpy(kv).cuda()
+            cap = n * 82 + 64 * 16 + 4096
+            d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+            for it in range(12):
+                out_len, index, st = s.sort_device_fixed(d_kv.data_ptr(), n, d_out.data_ptr(), cap)
+                assert out_len == len(exp["file_out"])
+                if it % 4 == 0:
+                    assert np.array_equal(d_out[:out_len].cpu().numpy(), np.frombuffer(exp["file_out"], dtype=np.uint8))
+                assert np.array_equal(index, exp["index"])
+    finally:
+        stop.set()
+        for t in threads:
+            t.join()
+
+
 def test_c2_fixed_multiple_collects_and_files(tmp_path):
     n, P = 30000, 7
     kv = O.gen_c2(100, n, seed=9)

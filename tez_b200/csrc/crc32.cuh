@@ -136,45 +136,42 @@ struct WarpLinearMap {
 // Per-thread update of the chunk-interleaved checksum for one 16-byte chunk (w0..w3): with W = "* x^32" (next word)
 // and S = "* x^(32*(4T-3))" (skip to this thread's next chunk) the textbook update is the dependent chain
 //        c' = S( W( W( W(c ^ w0) ^ w1 ) ^ w2 ) ^ w3 )            -- four table maps deep,
-// which left the emit kernels waiting on their own arithmetic (ncu: "wait" + short-scoreboard stalls with 5 warps per
-// scheduler).  Linearity gives the same value two maps deep:
+// which leaves a warp waiting on its own arithmetic.  Linearity gives the same value two maps deep:
 //        u = W(c ^ w0) ^ w1,   v = W(w2) ^ w3,   c' = (S W^2)(u) ^ S(v)
-// -- same number of look-ups (28 SHFL), half the latency, the two halves independent.  The thread's LAST chunk used to
-// end with W instead of S; here S is applied there too and the constant factor x^(128*(T-1)) it adds to every partial
-// is divided out once, in the per-lane alignment multiplier of the final fold (CrcTables::einv).
-#ifndef TEZGPU_CRC_ILP
-#define TEZGPU_CRC_ILP 1
-#endif
-struct CrcChunkFold {
+// -- same number of look-ups (28 SHFL), half the latency, the two halves independent.  The thread's LAST chunk ends
+// with W instead of S in the textbook form; the two-deep form applies S there too and the constant factor
+// x^(128*(T-1)) this adds to every partial is divided out once, in the per-lane alignment multiplier of the final fold
+// (CrcTables::einv; the inverse exists because the CRC-32 polynomial is primitive: tests/test_abi_cpu.py).
+// The third digit table costs 7 registers: measured on B200, kernels already at their register cap lose more to the
+// spills than they gain (k_emit_fast4 at 80 registers: 5.44 -> 6.94 ms, k_emit_fast4u 8.5 -> 9.8 ms), kernels with
+// headroom gain a little (k_emit_runs 8.98 -> 8.85 ms).  Hence a template flag per kernel.
+template <bool ILP>
+struct CrcChunkFoldT {
   WarpLinearMap w, s;
-#if TEZGPU_CRC_ILP
-  WarpLinearMap sw2;
-#endif
+  WarpLinearMap sw2;  // ILP only (dead and eliminated otherwise)
   uint32_t lane_pow;  // x^(128*(31-lane)) [* einv]: alignment of lane l's folded partials in the tile's final fold
   __device__ __forceinline__ void init(const CrcTables *__restrict__ t, uint32_t lane) {
     const uint32_t *gt = &t->slice[0][0], *ga = &t->advc[0][0];
     w.init([&](uint32_t x) { return gt[768 + (x & 0xFF)] ^ gt[512 + ((x >> 8) & 0xFF)] ^ gt[256 + ((x >> 16) & 0xFF)] ^ gt[x >> 24]; }, lane);
     s.init([&](uint32_t x) { return ga[x & 0xFF] ^ ga[256 + ((x >> 8) & 0xFF)] ^ ga[512 + ((x >> 16) & 0xFF)] ^ ga[768 + (x >> 24)]; }, lane);
     lane_pow = t->pow_word[4 * (31 - lane)];
-#if TEZGPU_CRC_ILP
-    const uint32_t *g2 = &t->advc2[0][0];
-    sw2.init([&](uint32_t x) { return g2[x & 0xFF] ^ g2[256 + ((x >> 8) & 0xFF)] ^ g2[512 + ((x >> 16) & 0xFF)] ^ g2[768 + (x >> 24)]; }, lane);
-    lane_pow = crc_multmodp(lane_pow, t->einv);
-#endif
+    if (ILP) {
+      const uint32_t *g2 = &t->advc2[0][0];
+      sw2.init([&](uint32_t x) { return g2[x & 0xFF] ^ g2[256 + ((x >> 8) & 0xFF)] ^ g2[512 + ((x >> 16) & 0xFF)] ^ g2[768 + (x >> 24)]; }, lane);
+      lane_pow = crc_multmodp(lane_pow, t->einv);
+    }
   }
   // all 32 lanes together (lanes without a chunk pass zeros, which stay zero); last = this is the thread's last chunk
   __device__ __forceinline__ uint32_t fold(uint32_t c, uint4 v, bool last) const {
-#if TEZGPU_CRC_ILP
-    (void)last;
-    const uint32_t u = w.apply(c ^ v.x) ^ v.y;
-    const uint32_t r = w.apply(v.z) ^ v.w;
-    return sw2.apply(u) ^ s.apply(r);
-#else
+    if (ILP) {
+      const uint32_t u = w.apply(c ^ v.x) ^ v.y;
+      const uint32_t r = w.apply(v.z) ^ v.w;
+      return sw2.apply(u) ^ s.apply(r);
+    }
     uint32_t x = w.apply(c ^ v.x) ^ v.y;
     x = w.apply(x) ^ v.z;
     x = w.apply(x) ^ v.w;
     return last ? w.apply(x) : s.apply(x);
-#endif
   }
 };
 

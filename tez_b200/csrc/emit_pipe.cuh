@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(FE_THREADS * SUBS, SUBS > 1 ? 1 : TEZGPU_EMIT4
   for (int i = threadIdx.x; i < 4 * 256; i += FE_THREADS * SUBS) s_adv128[i] = (&e.crc->adv128[0][0])[i];
   __syncthreads();
   if (tile >= ntiles) return;
-  CrcChunkFold cf;  // the chunk fold's linear maps as warp-resident digit tables (crc32.cuh)
+  CrcChunkFoldT<false> cf;  // the chunk fold's linear maps as warp-resident digit tables (crc32.cuh)
   cf.init(e.crc, lane);
   const uint32_t lane_pow = SUBS == 1 ? cf.lane_pow : e.crc->pow_word[4 * (31 - lane)];
   const WarpLinearMap &m_word = cf.w, &m_skip = cf.s;

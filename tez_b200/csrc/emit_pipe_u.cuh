@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(FE_THREADS, TEZGPU_EMIT4_MIN_CTAS) k_emit_fast
   if (tile >= ntiles) return;
   s_tab[tid] = e.crc->slice[0][tid];
   for (int i = tid; i < 4 * 256; i += FE_THREADS) s_adv128[i] = (&e.crc->adv128[0][0])[i];
-  CrcChunkFold cf;  // the chunk fold's linear maps as warp-resident digit tables (crc32.cuh)
+  CrcChunkFoldT<false> cf;  // the chunk fold's linear maps as warp-resident digit tables (crc32.cuh)
   cf.init(e.crc, lane);
   const uint32_t lane_pow = cf.lane_pow;
   const uint32_t img_base = (uint32_t)__cvta_generic_to_shared(s_img);

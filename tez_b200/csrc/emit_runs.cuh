@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(ER_THREADS, TEZGPU_EMIT_RUNS_MIN_CTAS) k_emit_
   // ================================================================== consumers (256 threads)
   const int tid = threadIdx.x - 32 * ER_PW, cwarp = tid >> 5;
   const uint32_t magic = (uint32_t)((1ull << 32) / rec_size) + 1u;
-  CrcChunkFold cf;  // the chunk fold's linear maps as warp-resident digit tables (crc32.cuh)
+  CrcChunkFoldT<true> cf;  // the chunk fold's linear maps as warp-resident digit tables (crc32.cuh)
   cf.init(e.crc, lane);
   const uint32_t lane_pow = cf.lane_pow;
   auto consumer_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(FE_THREADS) : "memory"); };

@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(ET_THREADS, TEZGPU_EMIT_TMA_MIN_CTAS) k_emit_t
     for (uint32_t b = 0; b < e.fixed_hdr_len; b++) hw[b >> 2] |= (uint32_t)e.fixed_hdr[b] << (8u * (b & 3u));
     kc.hdr = make_uint4(hw[0], hw[1], hw[2], hw[3]);
   }
-  CrcChunkFold cf;  // the chunk fold's linear maps as warp-resident digit tables (crc32.cuh)
+  CrcChunkFoldT<false> cf;  // the chunk fold's linear maps as warp-resident digit tables (crc32.cuh)
   cf.init(e.crc, lane);
   const uint32_t lane_pow = cf.lane_pow;
   auto consumer_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(FE_THREADS) : "memory"); };

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(CRCV_THREADS)
   s_tab[tid] = t->slice[0][tid];
   for (int i = tid; i < 4 * 256; i += CRCV_THREADS) s_adv128[i] = (&t->adv128[0][0])[i];
   // the two maps of the 16-byte-chunk interleave as warp-resident digit tables (crc32.cuh)
-  CrcChunkFold cf;
+  CrcChunkFoldT<true> cf;
   cf.init(t, lane);
   const uint32_t piece = blockIdx.x;
   uint32_t lo = 0, hi = nseg;  // last segment with piece_start[s] <= piece

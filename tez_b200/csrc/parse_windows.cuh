@@ -11,14 +11,10 @@
 // malformed record it met -- are the sequential reader's.  EXACTNESS never depends on the guesses below; only the number
 // of rounds does.
 //
-// Guess round: a walk started at a wrong byte usually dies within a few records (a byte decoded as a negative or huge
-// length), and one that survives falls into step with the true chain (from the first shared (position, state) on two
-// walks are identical).  So every window first tries candidate starts ws, ws+1, ... in both reader states until a walk
-// survives to the window's end, and publishes that walk's exit.  Measured on the CPU emulation (text keys, word-count
-// records, run-length encoded small records, 32 KiB windows): every window's exit is already exact after the guess
-// round, the first counting round confirms it (2 rounds).  Inputs where wrong walks survive without ever meeting the
-// true chain (multi-window run-length runs, records of random bytes larger than a window) converge one window per
-// round: after PW_MAX_ROUNDS the merger falls back to the sequential walker.
+// Guess round (pw_guess): every window first tries candidate starts until surviving walks agree on an exit, and
+// publishes it as the next window's entry; the counting rounds then confirm or repair (typically 2-3 rounds).  Inputs
+// where wrong walks survive without ever meeting the true chain (multi-window run-length runs, records larger than a
+// window) converge one window per round: after PW_MAX_ROUNDS the merger falls back to the sequential walker.
 //
 // Cost per round: every body byte is read once; typical total = guess + 1 counting + 1 emitting round.
 #pragma once
@@ -185,16 +181,36 @@ __device__ __forceinline__ PwWalk pw_walk(const uint8_t *__restrict__ seg, const
   return r;
 }
 
-// the exit of the first candidate start (offset, reader state) in window [ws, wend) whose walk survives to the window's
-// end (EOF markers count only where a well-formed body has them: in its last two bytes); PW_BAD when none does
+// Guess of a window's exit without knowing its entry: candidate starts ws, ws+1, ... in both reader states are walked
+// to the window's end.  Almost every wrong start dies within a few records (a byte decoded as a negative or absurd
+// length); one that survives usually fell into step with the true chain (two walks are identical from the first
+// (position, state) they share) and so reports the true exit.  The exceptions are flukes that decode a large length and
+// "survive" by jumping out of the window (measured on word-count data: 5 % of the windows when the first survivor is
+// taken, and such an exit, once published, is passed on from window to window and displaces correct guesses).  Hence:
+//   * EOF markers count only where a well-formed body has them (its last two bytes);
+//   * an exit beyond the NEXT window is only the fallback (records longer than a window are rare; when they exist every
+//     walk on the true chain reports the same far exit and the fallback is right);
+//   * the answer is the first exit that TWO surviving candidates agree on (0.2 % wrong on the same data; a wrong near
+//     exit heals in the next counting round because the walk started from it dies or falls into step).
+// Exactness never rests on any of this -- only the number of rounds does.
 __device__ __noinline__ uint64_t pw_guess(const uint8_t *__restrict__ seg, const PwSeg &sd, uint32_t s, uint64_t ws, uint64_t wend,
                                           bool last_win, const PwArrays &out) {
+  uint64_t far = PW_BAD, seen0 = PW_BAD, seen1 = PW_BAD, seen2 = PW_BAD;
   for (uint32_t o = 0; o < PW_MAX_TRIES && ws + o < wend; o++)
     for (uint64_t st = 0; st < 2; st++) {
       const PwWalk r = pw_walk<false>(seg, sd, s, wend, last_win, ((ws + o) << 1) | st, 0, ~0ull, 0, out);
-      if (r.exit_v != PW_BAD && !r.early_eof) return r.exit_v;
+      const uint64_t x = r.exit_v;
+      if (x == PW_BAD || r.early_eof) continue;
+      if (x != PW_EOF && (x >> 1) >= wend + PW_WINDOW) {
+        if (far == PW_BAD) far = x;
+        continue;
+      }
+      if (x == seen0 || x == seen1 || x == seen2) return x;
+      if (seen0 == PW_BAD) seen0 = x;
+      else if (seen1 == PW_BAD) seen1 = x;
+      else if (seen2 == PW_BAD) seen2 = x;
     }
-  return PW_BAD;
+  return seen0 != PW_BAD ? seen0 : far;
 }
 
 // One thread per window.

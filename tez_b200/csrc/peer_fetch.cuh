@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(FV_THREADS)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   s_tab[tid] = t->slice[0][tid];
   for (int i = tid; i < 4 * 256; i += FV_THREADS) s_adv128[i] = (&t->adv128[0][0])[i];
-  CrcChunkFold cf;
+  CrcChunkFoldT<true> cf;
   cf.init(t, lane);
   const uint32_t lane_pow = cf.lane_pow;
   __syncthreads();
