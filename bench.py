@@ -477,6 +477,7 @@ def config3(args):
     clk = clocks.stop()
     ms_step = sum(times) / len(times) * 1e3
     records, kv_bytes = m.counts()
+    parse_mode, parse_rounds = m.parse_info()
     assert records == sum(nrec) and kv_bytes == kv_in
     value = kv_bytes / (ms_step * 1e-3) / 1e9
     peak, peak_src = hbm_peak()
@@ -502,7 +503,8 @@ def config3(args):
                                    "2^24-word space, 8 B values, REPEAT_KEY output" % (nseg, args.c3_segment_mb),
                        "segments": nseg, "records": records, "input_bytes": in_bytes, "output_bytes": int(part),
                        "l2": "inputs larger than L2, no flush needed", "timing": "host clock around fully synchronised library calls",
-                       "generation_s": round(t_gen, 1)},
+                       "generation_s": round(t_gen, 1),
+                       "parser": {1: "window parser, %d counting rounds" % parse_rounds, 2: "sequential walker (window parser gave up)"}.get(parse_mode, str(parse_mode))},
             "clocks": clk, "e2e": None, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "whole merge step (parse + sort + emit)", "achieved": round(algo / (ms_step * 1e-3) / 1e9, 1),
                          "peak": peak, "unit": "GB/s", "frac": round(algo / (ms_step * 1e-3) / 1e9 / peak, 4), "traffic": None,
