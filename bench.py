@@ -504,7 +504,7 @@ def config3(args):
                        "segments": nseg, "records": records, "input_bytes": in_bytes, "output_bytes": int(part),
                        "l2": "inputs larger than L2, no flush needed", "timing": "host clock around fully synchronised library calls",
                        "generation_s": round(t_gen, 1),
-                       "parser": {1: "window parser, %d counting rounds" % parse_rounds, 2: "sequential walker (window parser gave up)"}.get(parse_mode, str(parse_mode))},
+                       "parser": {1: "window parser (guess / evaluate / chase), %d windows walked by hand" % parse_rounds, 2: "sequential walker (window parser gave up)"}.get(parse_mode, str(parse_mode))},
             "clocks": clk, "e2e": None, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "whole merge step (parse + sort + emit)", "achieved": round(algo / (ms_step * 1e-3) / 1e9, 1),
                          "peak": peak, "unit": "GB/s", "frac": round(algo / (ms_step * 1e-3) / 1e9 / peak, 4), "traffic": None,

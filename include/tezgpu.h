@@ -186,9 +186,9 @@ int32_t tezgpu_merge_reopen(tezgpu_merger *m, const tezgpu_segment *segs, uint32
 int32_t tezgpu_merge_set_check_for_same_keys(tezgpu_merger *m, int32_t check_for_same_keys);
 /* total records / key+value bytes of the merged stream */
 /* diagnostics: how the last open / reopen located the records -- mode 0: fixed framing, records addressed in place
- * (no parse); 1: parallel window parser (rounds = counting rounds it took); 2: sequential walker (one lane per
- * segment: the fallback when the window parser does not converge or meets a malformed record) */
-int32_t tezgpu_merge_parse_info(tezgpu_merger *m, int32_t *mode, int32_t *rounds);
+ * (no parse); 1: parallel window parser (by_hand = windows whose guessed entry was wrong and that the chase walked
+ * itself); 2: sequential walker (one lane per segment: taken when the window parser meets a malformed record) */
+int32_t tezgpu_merge_parse_info(tezgpu_merger *m, int32_t *mode, int32_t *by_hand);
 int32_t tezgpu_merge_counts(tezgpu_merger *m, uint64_t *records, uint64_t *kv_bytes);
 /* replaces the next()/getKey()/getValue()/isSameKey() loop: fills up to idx_cap records (key||value bytes appended to
  * out_kv, at most cap bytes); *n = 0 at end of stream */

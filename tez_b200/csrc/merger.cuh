@@ -679,27 +679,25 @@ class Merger {
     TG_CUDA(cudaMemcpyAsync(d_pwseg.p, ps.data(), (size_t)nseg * sizeof(PwSeg), cudaMemcpyHostToDevice, st));
     const uint32_t grid = (uint32_t)div_up(nwin, PW_THREADS);
     PwArrays none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    // guess round: every window publishes the exit of the first candidate walk that survives it
+    // guess -> evaluate from the guessed entries -> chase the true chain (parse_windows.cuh); one host round trip
+    TG_CUDA(cudaMemsetAsync(d_pwflags.p, 0, 64, st));
     k_parse_windows<0><<<grid, PW_THREADS, 0, st>>>(data, d_pwseg.as<PwSeg>(), nseg, nwin, nullptr, d_entry[0].as<uint64_t>(), nullptr, nullptr,
                                                     nullptr, d_pwflags.as<int>(), nullptr, nullptr, none);
-    launches++;
-    int cur = 0, flags[4] = {1, 0, 0, 0};
-    parse_rounds = 0;
-    while (flags[0] && parse_rounds < (int)PW_MAX_ROUNDS) {
-      TG_CUDA(cudaMemsetAsync(d_pwflags.p, 0, 64, st));
-      k_parse_windows<1><<<grid, PW_THREADS, 0, st>>>(data, d_pwseg.as<PwSeg>(), nseg, nwin, d_entry[cur].as<uint64_t>(),
-                                                      d_entry[cur ^ 1].as<uint64_t>(), d_wcount.as<uint32_t>(), d_wlast.as<uint64_t>(),
-                                                      nullptr, d_pwflags.as<int>(), nullptr, nullptr, none);
-      TG_CUDA(cudaGetLastError());
-      TG_CUDA(cudaMemcpyAsync(flags, d_pwflags.p, 16, cudaMemcpyDeviceToHost, st));
-      TG_CUDA(cudaStreamSynchronize(st));
-      launches++;
-      parse_rounds++;
-      cur ^= 1;
-    }
-    // not converged, or converged on a walk that died (malformed record / early EOF): the sequential walker decides
-    if (flags[0] || flags[1]) return false;
-    cur ^= 1;  // the entries the last (unchanged) round walked from
+    k_parse_windows<1><<<grid, PW_THREADS, 0, st>>>(data, d_pwseg.as<PwSeg>(), nseg, nwin, d_entry[0].as<uint64_t>(),
+                                                    d_entry[1].as<uint64_t>(), d_wcount.as<uint32_t>(), d_wlast.as<uint64_t>(),
+                                                    nullptr, d_pwflags.as<int>(), nullptr, nullptr, none);
+    k_parse_chase<<<(uint32_t)div_up(nseg, PW_CHASE_WARPS), 32 * PW_CHASE_WARPS, 0, st>>>(
+        data, d_pwseg.as<PwSeg>(), nseg, d_entry[0].as<uint64_t>(), d_entry[1].as<uint64_t>(), d_wcount.as<uint32_t>(),
+        d_wlast.as<uint64_t>(), d_pwflags.as<int>());
+    launches += 3;
+    TG_CUDA(cudaGetLastError());
+    int flags[4] = {0, 0, 0, 0};
+    TG_CUDA(cudaMemcpyAsync(flags, d_pwflags.p, 16, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaStreamSynchronize(st));
+    parse_rounds = flags[2];   // windows the chase had to walk by hand
+    // the sequential reader would reject a segment (or it ends early): the sequential walker reports it
+    if (flags[1]) return false;
+    const int cur = 0;         // d_entry[0] now holds the true entries
     // ---- record offsets of every window, totals
     const uint32_t nblk = (uint32_t)div_up(nwin, SCAN_TILE);
     pipe.blk.ensure(((size_t)nblk + 2) * 8);

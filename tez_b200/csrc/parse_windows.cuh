@@ -3,20 +3,31 @@
 // An IFile body is a chain: the position of record i+1 is only known once the vint lengths of record i are decoded,
 // and the format has no sync markers.  The walker of merger.cuh follows that chain with ONE lane per segment
 // (2.7 M dependent steps for a 64 MiB segment of 25-byte records).  Here every segment body is cut into windows of
-// PW_WINDOW bytes and ALL windows walk at once; a window publishes where its walk LEFT it (position + reader state),
-// which is the next window's entry.  Iterating
-//        entry_{t+1}[w+1] = exit( walk of window w from entry_t[w] ),      entry[first window] = body start,
-// reaches the fixed point after at most (#windows) rounds by induction (window w is exact after w rounds), and the
-// loop stops when a round changes no entry: then every entry is the true one, so that round's record counts -- and any
-// malformed record it met -- are the sequential reader's.  EXACTNESS never depends on the guesses below; only the number
-// of rounds does.
+// PW_WINDOW bytes that are walked at the same time:
 //
-// Guess round (pw_guess): every window first tries candidate starts until surviving walks agree on an exit, and
-// publishes it as the next window's entry; the counting rounds then confirm or repair (typically 2-3 rounds).  Inputs
-// where wrong walks survive without ever meeting the true chain (multi-window run-length runs, records larger than a
-// window) converge one window per round: after PW_MAX_ROUNDS the merger falls back to the sequential walker.
+//   1. guess    (k_parse_windows<0>)  every window guesses where the reader LEAVES it without knowing where it enters
+//                                      (pw_guess below); the guess of window w is the presumed entry of window w+1.
+//   2. evaluate (k_parse_windows<1>)  every window is walked from its presumed entry: record count, last full key,
+//                                      exit.  If the presumed entry is the true one, so are these.
+//   3. chase    (k_parse_chase)       one warp per segment follows the TRUE chain from the body start: window after
+//                                      window, "my entry equals the presumed entry" means the stored evaluation is the
+//                                      sequential reader's (32 windows are compared per step); where it is not -- a
+//                                      wrong guess, a few per thousand windows -- lane 0 walks that one window from
+//                                      the true entry and the chase goes on with its exit.
+//   4. emit     (k_parse_windows<2>)  entries are final; every window writes its records' metadata.
 //
-// Cost per round: every body byte is read once; typical total = guess + 1 counting + 1 emitting round.
+// EXACTNESS rests on step 3 alone: the chase reproduces the sequential reader by induction from the first window; the
+// guesses only decide how many windows it has to walk by hand (all of them in the worst case, which is the sequential
+// walker's cost).  A malformed record, EOF markers before the body's end or a body that does not end with them makes
+// the chase give up and the merger takes the sequential walker, which reports the error the way IFile.Reader does.
+//
+// An earlier version iterated entry_{t+1}[w+1] = exit(walk from entry_t[w]) to a fixed point.  On word-count data a
+// wrong guess starts a walk in the "previous record was a repeat" state that reads every byte it lands on as a value
+// length, hops on without ever meeting the true chain or dying, and is handed from window to window one round at a
+// time, forever ahead of the correction behind it: the iteration did not converge within any useful number of rounds.
+//
+// Cost: guess ~2 walks + a few dozen short-lived candidate walks per window, evaluate 1, emit 1 (every body byte is
+// read about four times, by all SMs), chase ~(#windows / 32) steps per segment + the hand-walked windows.
 #pragma once
 #include "common.cuh"
 
@@ -29,7 +40,7 @@ constexpr uint32_t PW_MAX_TRIES = 8192;   // candidate start offsets per window 
 constexpr int PW_THREADS = 128;
 constexpr uint64_t PW_EOF = ~0ull;        // the reader met the EOF markers before this window
 constexpr uint64_t PW_BAD = ~0ull - 1;    // the walk that produced this entry met a malformed record
-constexpr uint32_t PW_MAX_ROUNDS = 6;
+constexpr int PW_CHASE_WARPS = 4;          // segments per CTA of k_parse_chase
 
 struct PwSeg {
   uint64_t off;        // segment start in the data buffer
@@ -214,18 +225,10 @@ __device__ __noinline__ uint64_t pw_guess(const uint8_t *__restrict__ seg, const
 }
 
 // One thread per window.
-//   MODE 0  guess round: first windows walk from the body start, every other window publishes pw_guess as the next
-//           window's entry.
-//   MODE 1  counting round: walks from entry_in, publishes the exit, sets flags[0] when it differs from the entry the
-//           next window used, records the window's record count and its last full key.  A walk that DIES (malformed
-//           record, EOF markers before the body's end, or an entry that is itself the trace of a dead walk) was started
-//           from a wrong entry -- or the data is malformed: it publishes pw_guess instead of its death (a dead exit
-//           would travel on, one window per round, long after the wrong entry that caused it was corrected) and raises
-//           flags[1].  A round with flags[0] == 0 and flags[1] == 0 walked every window from its true entry (induction
-//           from the first window) and met no malformed record: its counts are the sequential reader's.  flags[1] in
-//           a round that changed nothing means malformed input (or an early EOF): the caller takes the sequential
-//           walker, which reports it the way IFile.Reader does.
-//   MODE 2  emitting round: entries are final; writes the per-record metadata at rec_base[w]...
+//   MODE 0  guess: first windows walk from the body start (their exit is exact), every other window publishes pw_guess
+//           as the next window's presumed entry.
+//   MODE 1  evaluate: walks from the presumed entry; stores the exit, the record count and the last full key.
+//   MODE 2  emit: entries are final (k_parse_chase); writes the per-record metadata at rec_base[w]...
 template <int MODE>
 __global__ void __launch_bounds__(PW_THREADS)
     k_parse_windows(const uint8_t *__restrict__ data, const PwSeg *__restrict__ segs, uint32_t nseg,
@@ -259,16 +262,10 @@ __global__ void __launch_bounds__(PW_THREADS)
       wcount[w] = r.n;
       wlastkey[2 * (uint64_t)w] = r.lk_off;
       wlastkey[2 * (uint64_t)w + 1] = r.lk_len;
-      const uint64_t e_in = (k == 0) ? (sd.body0 << 1) : entry_in[w];
-      // the stream must end with the EOF markers, in the last window, and nowhere else
-      const bool died = r.exit_v == PW_BAD || e_in == PW_EOF || r.early_eof || (last_win ? r.exit_v != PW_EOF : r.exit_v == PW_EOF);
-      if (died) atomicMax(flags + 1, (int)s + 1);
-      if (!last_win) {
-        const uint64_t x = (died && k > 0) ? pw_guess(seg, sd, s, ws, wend, last_win, out) : r.exit_v;
-        if (entry_in[w + 1] != x) flags[0] = 1;
-        entry_out[w + 1] = x;
-      }
-      if (k == 0) entry_out[w] = sd.body0 << 1;
+      // a walk that met a malformed record, or EOF markers anywhere but at the end of the last window, is recorded as
+      // dead: if its entry turns out to be the true one the chase reports the segment, otherwise it is walked again
+      const bool dead = r.exit_v == PW_BAD || r.early_eof || (last_win ? r.exit_v != PW_EOF : r.exit_v == PW_EOF);
+      entry_out[w] = dead ? PW_BAD : r.exit_v;   // MODE 1: entry_out = exit of every window
     } else {
       if (r.exit_v == PW_BAD) atomicMax(flags + 1, (int)s + 1);
       my_bytes = r.bytes;
@@ -279,6 +276,75 @@ __global__ void __launch_bounds__(PW_THREADS)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) my_bytes += __shfl_xor_sync(0xffffffffu, my_bytes, o);
     if ((threadIdx.x & 31) == 0 && my_bytes) atomicAdd(kv_total, (unsigned long long)my_bytes);
+  }
+}
+
+// Follows the true chain of every segment through the evaluated windows (one warp per segment).
+//   entry[w]  in: presumed entry of window w (guess), out: true entry
+//   wexit[w]  exit of the walk from entry[w]; wcount / wlastkey likewise -- rewritten for hand-walked windows
+//   flags[1]  segment + 1 of a segment the sequential reader would reject (or that ends early): caller falls back
+//   flags[2]  number of windows walked by hand (diagnostics)
+__global__ void __launch_bounds__(32 * PW_CHASE_WARPS)
+    k_parse_chase(const uint8_t *__restrict__ data, const PwSeg *__restrict__ segs, uint32_t nseg, uint64_t *__restrict__ entry,
+                  uint64_t *__restrict__ wexit, uint32_t *__restrict__ wcount, uint64_t *__restrict__ wlastkey, int *__restrict__ flags) {
+  const uint32_t s = blockIdx.x * PW_CHASE_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (s >= nseg) return;
+  const PwSeg sd = segs[s];
+  const uint8_t *__restrict__ seg = data + sd.off;
+  PwArrays none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint64_t e = sd.body0 << 1;   // true entry of window k
+  uint32_t k = 0, by_hand = 0;
+  bool bad = false;
+  while (k < sd.nwin && !bad) {
+    const uint32_t w = sd.win0 + k + lane;
+    const bool in = k + lane < sd.nwin;
+    const uint64_t eg = in ? entry[w] : PW_BAD;
+    const uint64_t x = in ? wexit[w] : PW_BAD;
+    // lane i: window k+i hands its exit to window k+i+1 unchanged (the last window has nobody to hand to)
+    uint64_t eg_next = __shfl_down_sync(0xffffffffu, eg, 1);
+    if (lane == 31) eg_next = (k + 32 < sd.nwin) ? entry[w + 1] : PW_BAD;
+    const bool is_last = in && (k + lane + 1 == sd.nwin);
+    const bool alive = in && x != PW_BAD;
+    const bool hands_on = alive && !is_last && x == eg_next;
+    const uint64_t eg0 = __shfl_sync(0xffffffffu, eg, 0);
+    if (e == eg0) {
+      // the stored evaluations are the reader's for windows k .. k+i, i = first lane that does not hand on
+      const uint32_t stop = __ballot_sync(0xffffffffu, !hands_on);
+      const int i = __ffs((int)stop) - 1;       // >= 0: lanes past the segment never hand on
+      const bool alive_i = __shfl_sync(0xffffffffu, (int)alive, i) != 0;
+      const bool last_i = __shfl_sync(0xffffffffu, (int)is_last, i) != 0;
+      const uint64_t x_i = __shfl_sync(0xffffffffu, x, i);
+      if (!alive_i) { bad = true; break; }      // the reader itself meets the malformed record / misplaced EOF
+      if (last_i) { k = sd.nwin; break; }       // reached the end of the body (exit == EOF, checked when evaluated)
+      e = x_i;
+      k += (uint32_t)i + 1;
+    } else {
+      // wrong guess: lane 0 walks window k from the true entry
+      uint64_t xe = PW_BAD;
+      if (lane == 0) {
+        const uint64_t ws = sd.body0 + (uint64_t)k * PW_WINDOW;
+        const uint64_t wend = min(sd.body_end, ws + PW_WINDOW);
+        const bool last_win = (k + 1 == sd.nwin);
+        const PwWalk r = pw_walk<false>(seg, sd, s, wend, last_win, e, 0, ~0ull, 0, none);
+        const bool dead = r.exit_v == PW_BAD || r.early_eof || (last_win ? r.exit_v != PW_EOF : r.exit_v == PW_EOF);
+        const uint32_t w0 = sd.win0 + k;
+        entry[w0] = e;
+        wexit[w0] = dead ? PW_BAD : r.exit_v;
+        wcount[w0] = r.n;
+        wlastkey[2 * (uint64_t)w0] = r.lk_off;
+        wlastkey[2 * (uint64_t)w0 + 1] = r.lk_len;
+        xe = dead ? PW_BAD : r.exit_v;
+      }
+      xe = __shfl_sync(0xffffffffu, xe, 0);
+      by_hand++;
+      if (xe == PW_BAD) { bad = true; break; }
+      e = xe;
+      k++;
+    }
+  }
+  if (lane == 0) {
+    if (bad) atomicMax(flags + 1, (int)s + 1);
+    if (by_hand) atomicAdd(flags + 2, (int)by_hand);
   }
 }
 

@@ -179,7 +179,7 @@ class GpuMerger:
         check(self.L.tezgpu_merge_set_check_for_same_keys(self.h, 1 if on else 0))
 
     def parse_info(self):
-        """(mode, rounds) of the last open: 0 records addressed in place, 1 window parser, 2 sequential walker."""
+        """(mode, windows walked by hand) of the last open: 0 records addressed in place, 1 window parser, 2 sequential walker."""
         m, r = C.c_int32(), C.c_int32()
         check(self.L.tezgpu_merge_parse_info(self.h, C.byref(m), C.byref(r)))
         return m.value, r.value
