@@ -681,8 +681,8 @@ class Merger {
     PwArrays none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // guess -> evaluate from the guessed entries -> chase the true chain (parse_windows.cuh); one host round trip
     TG_CUDA(cudaMemsetAsync(d_pwflags.p, 0, 64, st));
-    k_parse_windows<0><<<grid, PW_THREADS, 0, st>>>(data, d_pwseg.as<PwSeg>(), nseg, nwin, nullptr, d_entry[0].as<uint64_t>(), nullptr, nullptr,
-                                                    nullptr, d_pwflags.as<int>(), nullptr, nullptr, none);
+    k_parse_guess<<<(uint32_t)div_up((uint64_t)nwin * 32, PW_GUESS_THREADS), PW_GUESS_THREADS, 0, st>>>(data, d_pwseg.as<PwSeg>(), nseg, nwin,
+                                                                                                        d_entry[0].as<uint64_t>());
     k_parse_windows<1><<<grid, PW_THREADS, 0, st>>>(data, d_pwseg.as<PwSeg>(), nseg, nwin, d_entry[0].as<uint64_t>(),
                                                     d_entry[1].as<uint64_t>(), d_wcount.as<uint32_t>(), d_wlast.as<uint64_t>(),
                                                     nullptr, d_pwflags.as<int>(), nullptr, nullptr, none);

@@ -5,8 +5,8 @@
 // (2.7 M dependent steps for a 64 MiB segment of 25-byte records).  Here every segment body is cut into windows of
 // PW_WINDOW bytes that are walked at the same time:
 //
-//   1. guess    (k_parse_windows<0>)  every window guesses where the reader LEAVES it without knowing where it enters
-//                                      (pw_guess below); the guess of window w is the presumed entry of window w+1.
+//   1. guess    (k_parse_guess)       every window guesses where the reader LEAVES it without knowing where it enters
+//                                      (k_parse_guess below); the guess of window w is the presumed entry of window w+1.
 //   2. evaluate (k_parse_windows<1>)  every window is walked from its presumed entry: record count, last full key,
 //                                      exit.  If the presumed entry is the true one, so are these.
 //   3. chase    (k_parse_chase)       one warp per segment follows the TRUE chain from the body start: window after
@@ -26,8 +26,8 @@
 // length, hops on without ever meeting the true chain or dying, and is handed from window to window one round at a
 // time, forever ahead of the correction behind it: the iteration did not converge within any useful number of rounds.
 //
-// Cost: guess ~2 walks + a few dozen short-lived candidate walks per window, evaluate 1, emit 1 (every body byte is
-// read about four times, by all SMs), chase ~(#windows / 32) steps per segment + the hand-walked windows.
+// Cost: guess = one or two rounds of 32 concurrent candidate walks per window (a warp; most die at once, the survivors
+// share their loads), evaluate 1 walk, emit 1 walk; chase ~(#windows / 32) steps per segment + the hand-walked windows.
 #pragma once
 #include "common.cuh"
 
@@ -40,6 +40,7 @@ constexpr uint32_t PW_MAX_TRIES = 8192;   // candidate start offsets per window 
 constexpr int PW_THREADS = 128;
 constexpr uint64_t PW_EOF = ~0ull;        // the reader met the EOF markers before this window
 constexpr uint64_t PW_BAD = ~0ull - 1;    // the walk that produced this entry met a malformed record
+constexpr int PW_GUESS_THREADS = 128;      // k_parse_guess: four windows per CTA, one warp each
 constexpr int PW_CHASE_WARPS = 4;          // segments per CTA of k_parse_chase
 
 struct PwSeg {
@@ -192,41 +193,76 @@ __device__ __forceinline__ PwWalk pw_walk(const uint8_t *__restrict__ seg, const
   return r;
 }
 
-// Guess of a window's exit without knowing its entry: candidate starts ws, ws+1, ... in both reader states are walked
-// to the window's end.  Almost every wrong start dies within a few records (a byte decoded as a negative or absurd
-// length); one that survives usually fell into step with the true chain (two walks are identical from the first
-// (position, state) they share) and so reports the true exit.  The exceptions are flukes that decode a large length and
-// "survive" by jumping out of the window (measured on word-count data: 5 % of the windows when the first survivor is
-// taken, and such an exit, once published, is passed on from window to window and displaces correct guesses).  Hence:
+// Guess of a window's exit without knowing its entry (k_parse_guess, one WARP per window): candidate starts ws, ws+1,
+// ... in both reader states are walked to the window's end, 32 candidates at a time (lane l: offset l/2, state l&1).
+// Almost every wrong start dies within a few records (a byte decoded as a negative or absurd length); one that
+// survives usually fell into step with the true chain (two walks are identical from the first (position, state) they
+// share) and so reports the true exit.  The exceptions are flukes that decode a large length and "survive" by jumping
+// out of the window, and walks in the "previous record was a repeat" state, which read every byte they land on as a
+// value length and hop on for a long time (measured on word-count data: 5 % wrong guesses when the first survivor is
+// taken).  Hence:
 //   * EOF markers count only where a well-formed body has them (its last two bytes);
 //   * an exit beyond the NEXT window is only the fallback (records longer than a window are rare; when they exist every
 //     walk on the true chain reports the same far exit and the fallback is right);
-//   * the answer is the first exit that TWO surviving candidates agree on (0.2 % wrong on the same data; a wrong near
-//     exit heals in the next counting round because the walk started from it dies or falls into step).
-// Exactness never rests on any of this -- only the number of rounds does.
-__device__ __noinline__ uint64_t pw_guess(const uint8_t *__restrict__ seg, const PwSeg &sd, uint32_t s, uint64_t ws, uint64_t wend,
-                                          bool last_win, const PwArrays &out) {
-  uint64_t far = PW_BAD, seen0 = PW_BAD, seen1 = PW_BAD, seen2 = PW_BAD;
-  for (uint32_t o = 0; o < PW_MAX_TRIES && ws + o < wend; o++)
-    for (uint64_t st = 0; st < 2; st++) {
-      const PwWalk r = pw_walk<false>(seg, sd, s, wend, last_win, ((ws + o) << 1) | st, 0, ~0ull, 0, out);
-      const uint64_t x = r.exit_v;
-      if (x == PW_BAD || r.early_eof) continue;
-      if (x != PW_EOF && (x >> 1) >= wend + PW_WINDOW) {
-        if (far == PW_BAD) far = x;
-        continue;
-      }
-      if (x == seen0 || x == seen1 || x == seen2) return x;
-      if (seen0 == PW_BAD) seen0 = x;
-      else if (seen1 == PW_BAD) seen1 = x;
-      else if (seen2 == PW_BAD) seen2 = x;
+//   * the answer is the first exit that TWO surviving candidates agree on (0.2-0.4 % wrong on the same data).
+// Exactness never rests on any of this (k_parse_chase) -- only the number of windows walked a second time does.
+__global__ void __launch_bounds__(PW_GUESS_THREADS)
+    k_parse_guess(const uint8_t *__restrict__ data, const PwSeg *__restrict__ segs, uint32_t nseg, uint32_t nwin_total,
+                  uint64_t *__restrict__ entry_out) {
+  const uint32_t w = (blockIdx.x * PW_GUESS_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= nwin_total) return;
+  const uint32_t s = pw_seg_of(segs, nseg, w);
+  const PwSeg sd = segs[s];
+  const uint8_t *__restrict__ seg = data + sd.off;
+  const uint32_t k = w - sd.win0;
+  const uint64_t ws = sd.body0 + (uint64_t)k * PW_WINDOW;
+  const uint64_t wend = min(sd.body_end, ws + PW_WINDOW);
+  const bool last_win = (k + 1 == sd.nwin);
+  PwArrays none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (k == 0 && lane == 0) entry_out[w] = sd.body0 << 1;
+  if (last_win) return;                       // nobody to hand an exit to
+  if (k == 0) {                               // the first window's entry is known: its exit is exact
+    if (lane == 0) entry_out[w + 1] = pw_walk<false>(seg, sd, s, wend, false, sd.body0 << 1, 0, ~0ull, 0, none).exit_v;
+    return;
+  }
+  uint64_t far = PW_BAD, seen0 = PW_BAD, seen1 = PW_BAD, seen2 = PW_BAD, result = PW_BAD;
+  bool done = false;
+  for (uint32_t o0 = 0; o0 < PW_MAX_TRIES && ws + o0 < wend && !done; o0 += 16) {
+    const uint64_t start = ws + o0 + (lane >> 1);
+    uint64_t x = PW_BAD;
+    if (start < wend) {
+      const PwWalk r = pw_walk<false>(seg, sd, s, wend, false, (start << 1) | (uint64_t)(lane & 1u), 0, ~0ull, 0, none);
+      x = r.early_eof ? PW_BAD : r.exit_v;
+      if (x == PW_EOF) x = PW_BAD;            // EOF inside a window that is not the last one
     }
-  return seen0 != PW_BAD ? seen0 : far;
+    __syncwarp();
+    const bool is_far = x != PW_BAD && (x >> 1) >= wend + PW_WINDOW;
+    const bool near = x != PW_BAD && !is_far;
+    const uint32_t fm = __ballot_sync(0xffffffffu, is_far);
+    if (far == PW_BAD && fm) far = __shfl_sync(0xffffffffu, x, __ffs((int)fm) - 1);
+    const uint32_t nm = __ballot_sync(0xffffffffu, near);
+    if (nm) {
+      uint32_t cnt = 0;
+      if (near) cnt = (uint32_t)__popc(__match_any_sync(nm, x)) + ((x == seen0 || x == seen1 || x == seen2) ? 1u : 0u);
+      const uint32_t am = __ballot_sync(0xffffffffu, near && cnt >= 2);
+      if (am) {
+        result = __shfl_sync(0xffffffffu, x, __ffs((int)am) - 1);
+        done = true;
+      } else {
+        for (uint32_t m = nm; m && seen2 == PW_BAD; m &= m - 1) {   // every survivor so far stands alone: remember three
+          const uint64_t v = __shfl_sync(0xffffffffu, x, __ffs((int)m) - 1);
+          if (seen0 == PW_BAD) seen0 = v;
+          else if (seen1 == PW_BAD) seen1 = v;
+          else seen2 = v;
+        }
+      }
+    }
+  }
+  if (!done) result = seen0 != PW_BAD ? seen0 : far;
+  if (lane == 0) entry_out[w + 1] = result;
 }
 
 // One thread per window.
-//   MODE 0  guess: first windows walk from the body start (their exit is exact), every other window publishes pw_guess
-//           as the next window's presumed entry.
 //   MODE 1  evaluate: walks from the presumed entry; stores the exit, the record count and the last full key.
 //   MODE 2  emit: entries are final (k_parse_chase); writes the per-record metadata at rec_base[w]...
 template <int MODE>
@@ -247,18 +283,10 @@ __global__ void __launch_bounds__(PW_THREADS)
     const uint64_t ws = sd.body0 + (uint64_t)k * PW_WINDOW;
     const uint64_t wend = min(sd.body_end, ws + PW_WINDOW);
     const bool last_win = (k + 1 == sd.nwin);
-    PwWalk r;
-    if (MODE == 0 && k > 0) {
-      r.exit_v = last_win ? PW_EOF : pw_guess(seg, sd, s, ws, wend, last_win, out);
-    } else {
-      const uint64_t e = (k == 0) ? (sd.body0 << 1) : entry_in[w];
-      r = pw_walk<EMIT>(seg, sd, s, wend, last_win, e, EMIT ? rec_base[w] : 0, EMIT ? carry[2 * (uint64_t)w] : ~0ull,
-                        EMIT ? carry[2 * (uint64_t)w + 1] : 0, out);
-    }
-    if (MODE == 0) {
-      if (!last_win) entry_out[w + 1] = r.exit_v;
-      if (k == 0) entry_out[w] = sd.body0 << 1;
-    } else if (MODE == 1) {
+    const uint64_t e = (k == 0) ? (sd.body0 << 1) : entry_in[w];
+    const PwWalk r = pw_walk<EMIT>(seg, sd, s, wend, last_win, e, EMIT ? rec_base[w] : 0, EMIT ? carry[2 * (uint64_t)w] : ~0ull,
+                                   EMIT ? carry[2 * (uint64_t)w + 1] : 0, out);
+    if (MODE == 1) {
       wcount[w] = r.n;
       wlastkey[2 * (uint64_t)w] = r.lk_off;
       wlastkey[2 * (uint64_t)w + 1] = r.lk_len;
