@@ -338,7 +338,12 @@ __global__ void __launch_bounds__(32 * PW_CHASE_WARPS)
     if (e == eg0) {
       // the stored evaluations are the reader's for windows k .. k+i, i = first lane that does not hand on
       const uint32_t stop = __ballot_sync(0xffffffffu, !hands_on);
-      const int i = __ffs((int)stop) - 1;       // >= 0: lanes past the segment never hand on
+      if (stop == 0) {                          // all 32 windows hand on: the chain enters window k+32 as guessed
+        e = __shfl_sync(0xffffffffu, x, 31);
+        k += 32;
+        continue;
+      }
+      const int i = __ffs((int)stop) - 1;
       const bool alive_i = __shfl_sync(0xffffffffu, (int)alive, i) != 0;
       const bool last_i = __shfl_sync(0xffffffffu, (int)is_last, i) != 0;
       const uint64_t x_i = __shfl_sync(0xffffffffu, x, i);

@@ -622,8 +622,18 @@ class SortPipeline {
         }
         k_crc_combine<<<(uint32_t)div_up(tiles, 256), 256, 0, stream>>>(fp.tile_crc, (uint32_t)tiles, d_crc, seg_crc.as<uint32_t>());
         launches++;
-      } else if (fixed_emit) k_emit<true><<<(uint32_t)tiles, EMIT_THREADS, 0, stream>>>(e);
-      else k_emit<false><<<(uint32_t)tiles, EMIT_THREADS, 0, stream>>>(e);
+      } else {
+        // general kernel, persistent CTAs (as many as fit the device at once)
+        static int per_sm_fixed = 0, per_sm_var = 0;
+        if (!per_sm_fixed) {
+          TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_fixed, k_emit<true>, EMIT_THREADS, 0));
+          TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_var, k_emit<false>, EMIT_THREADS, 0));
+        }
+        const uint32_t cap = (uint32_t)num_sms * (uint32_t)std::max(1, fixed_emit ? per_sm_fixed : per_sm_var);
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(tiles, cap);
+        if (fixed_emit) k_emit<true><<<grid, EMIT_THREADS, 0, stream>>>(e);
+        else k_emit<false><<<grid, EMIT_THREADS, 0, stream>>>(e);
+      }
       launches++;
       TG_CUDA(cudaGetLastError());
     }

@@ -867,8 +867,15 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(EmitParams e) {
   __shared__ uint32_t s_info[8];
 
   const int tid = threadIdx.x;
-  const uint32_t tile = blockIdx.x;
-  if (tile >= e.tile_start[e.P]) return;
+  for (int i = tid; i < 4 * 256; i += EMIT_THREADS) {
+    s_tab[i] = (&e.crc->slice[0][0])[i];
+    s_adv[i] = (&e.crc->adv[0][0])[i];
+  }
+  const uint32_t ntiles = e.tile_start[e.P];
+  // persistent CTAs: with small records a tile is a few KB of output and there are millions of them -- the checksum
+  // tables are loaded once per CTA, not once per tile
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  __syncthreads();  // the previous tile's shared state is dead (and, first time round, the tables are in place)
 
   // ---- locate the tile: partition p, records [r0, r0 + nr)
   if (tid == 0) {
@@ -880,10 +887,6 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(EmitParams e) {
     // skip empty partitions that share the same tile_start
     while (lo + 1 < e.P && e.tile_start[lo + 1] <= tile) lo++;
     s_info[0] = (uint32_t)lo;
-  }
-  for (int i = tid; i < 4 * 256; i += EMIT_THREADS) {
-    s_tab[i] = (&e.crc->slice[0][0])[i];
-    s_adv[i] = (&e.crc->adv[0][0])[i];
   }
   __syncthreads();
   const uint32_t p = s_info[0];
@@ -1084,6 +1087,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) k_emit(EmitParams e) {
     __syncthreads();
     done += plen;
   }
+  }  // tiles
 }
 
 // writes the 4-byte big-endian checksum of every segment (and the constant 10-byte empty segments)
