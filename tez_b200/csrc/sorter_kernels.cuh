@@ -422,8 +422,25 @@ __device__ __forceinline__ int compare_keys_from(const Records &r, uint32_t ra, 
   uint32_t sa = key_content_skip(r.cmp, a, la), sb = key_content_skip(r.cmp, b, lb);
   a += sa; b += sb; la -= sa; lb -= sb;
   uint32_t nmin = la < lb ? la : lb;
-  for (uint32_t i = depth; i < nmin; i++) {
-    uint32_t x = norm_byte(r.cmp, a, i), y = norm_byte(r.cmp, b, i);
+  uint32_t i = depth;
+  if (i == 0 && nmin > 0) {   // byte 0 is the only one a comparator normalises (sign bit of IntWritable / LongWritable)
+    uint32_t x = norm_byte(r.cmp, a, 0), y = norm_byte(r.cmp, b, 0);
+    if (x != y) return x < y ? -1 : 1;
+    i = 1;
+  }
+  // eight bytes per step: sixteen independent byte loads (any alignment, never past the keys) instead of a chain of
+  // load-compare-branch per byte -- equal keys (the common case when merging word counts) are compared to their end
+  for (; i + 8 <= nmin; i += 8) {
+    uint64_t x = 0, y = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      x = (x << 8) | a[i + q];
+      y = (y << 8) | b[i + q];
+    }
+    if (x != y) return x < y ? -1 : 1;
+  }
+  for (; i < nmin; i++) {
+    uint32_t x = a[i], y = b[i];
     if (x != y) return x < y ? -1 : 1;
   }
   return la < lb ? -1 : (la == lb ? 0 : 1);
@@ -454,18 +471,33 @@ __device__ __forceinline__ void tie_fix_group(const Records &r, const uint32_t *
   my_ties += sz;
   uint32_t idx[TIE_SMALL_MAX];
   for (uint32_t j = 0; j < sz; j++) idx[j] = order[i + j];
-  // stable insertion sort (equal keys keep their original relative order)
+  // stable insertion sort (equal keys keep their original relative order).  eq bit j = "idx[j] equals idx[j-1]" is kept
+  // up to date from the comparisons the sort makes anyway (a merge of word counts is mostly duplicates: one comparison
+  // per record instead of two): the element an insertion stops at compares <= v, everything shifted right compares > v,
+  // and whatever is later inserted between two equal neighbours equals both.
+  uint32_t eq = 0;
   for (uint32_t a = 1; a < sz; a++) {
     const uint32_t v = idx[a];
     uint32_t b = a;
-    while (b > 0 && compare_keys_from(r, idx[b - 1], v, depth) > 0) { idx[b] = idx[b - 1]; b--; }
+    int c = 1;
+    while (b > 0) {
+      c = compare_keys_from(r, idx[b - 1], v, depth);
+      if (c <= 0) break;
+      idx[b] = idx[b - 1];
+      b--;
+    }
     idx[b] = v;
+    // bits b+1 .. a-1 (pairs that moved together) shift up by one, bit b+1 (v < its new successor) and bit b are rewritten
+    const uint32_t low = eq & ((1u << b) - 1u);
+    const uint32_t high = b < a ? ((eq >> (b + 1)) << (b + 2)) : 0u;
+    eq = low | high | ((b > 0 && c == 0) ? (1u << b) : 0u);
   }
   order[i] = idx[0];
   for (uint32_t j = 1; j < sz; j++) {
     order[i + j] = idx[j];
-    if (compare_keys_from(r, idx[j - 1], idx[j], depth) == 0) { same[i + j] = 1; my_dups++; }
+    if ((eq >> j) & 1u) same[i + j] = 1;
   }
+  my_dups += (uint32_t)__popc(eq);
 }
 
 // The streaming part (all warps) queues group heads in shared memory; once a few hundred are queued every thread takes
