@@ -253,6 +253,35 @@ typedef struct tezgpu_fetch_segment {
 int32_t tezgpu_fetch_segments_verified(int32_t device, const tezgpu_fetch_segment *segs, uint32_t n, void *stream,
                                        float *ms_kernel);
 
+/* ---- the ShuffleHandler <-> FetcherOrderedGrouped wire format, for consumers outside the NVLink domain
+ * (and unmodified fetchers).  Per map output and reducer: ShuffleHeader (OG/ShuffleHeader.java:101-106:
+ * Text.writeString(mapId), vlong compressedLength = partLength, vlong uncompressedLength = rawLength, vint forReduce)
+ * followed by partLength bytes of the partition's IFile segment (OG/FetcherOrderedGrouped.java:437-632 reads exactly
+ * that).  Host-side framing; the segment bytes are copied out of the device-resident file.out. */
+uint64_t tezgpu_shuffle_header_size(const char *map_id, int64_t part_len, int64_t raw_len, int32_t reduce);
+int32_t tezgpu_shuffle_header_write(const char *map_id, int64_t part_len, int64_t raw_len, int32_t reduce, uint8_t *out,
+                                    uint64_t cap, uint64_t *len);
+/* ShuffleHeader.readFields (:82-87, map id at most 1000 bytes); consumed = header bytes */
+int32_t tezgpu_shuffle_header_read(const uint8_t *in, uint64_t avail, char *map_id, uint64_t map_id_cap, int64_t *part_len,
+                                   int64_t *raw_len, int32_t *reduce, uint64_t *consumed);
+/* response body for reducers [reduce0, reduce0 + nreduce) of ONE map output whose file.out lives in device memory:
+ * index = the 3 * P int64 triples (start, rawLength, partLength) of its spill record; out = host (ideally pinned) buffer
+ * of at least tezgpu_shuffle_serve_bound bytes; returns after the copies completed */
+uint64_t tezgpu_shuffle_serve_bound(const char *map_id, const int64_t *index, int32_t reduce0, int32_t nreduce);
+int32_t tezgpu_shuffle_serve(int32_t device, const void *d_file_out, const int64_t *index, const char *map_id,
+                             int32_t reduce0, int32_t nreduce, uint8_t *out, uint64_t cap, uint64_t *len, void *stream);
+/* consumer side: splits a response body into its segments (what copyMapOutput does header by header); every segment is
+ * in[offset .. offset + part_len) and can go to tezgpu_merge_open as a host segment with TEZGPU_SEG_HAS_HEADER */
+typedef struct tezgpu_wire_segment {
+  char map_id[1008];
+  int64_t part_len;
+  int64_t raw_len;
+  uint64_t offset;
+  int32_t reduce;
+  int32_t reserved;
+} tezgpu_wire_segment;
+int32_t tezgpu_shuffle_receive(const uint8_t *in, uint64_t len, tezgpu_wire_segment *segs, uint32_t cap, uint32_t *n);
+
 /* diagnostics: host-side emulation of the device's tiled CRC algebra (same tables, no GPU needed) */
 uint32_t tezgpu_debug_crc_emulate(const uint8_t *body, uint64_t len, uint32_t piece_bytes, uint32_t lead);
 

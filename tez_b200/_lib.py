@@ -15,6 +15,12 @@ class Conf(C.Structure):
                 ("fixed_key_len", C.c_uint32), ("fixed_val_len", C.c_uint32), ("mem_budget_bytes", C.c_uint64)]
 
 
+class WireSegment(C.Structure):
+    """tezgpu_wire_segment (include/tezgpu.h)"""
+    _fields_ = [("map_id", C.c_char * 1008), ("part_len", C.c_int64), ("raw_len", C.c_int64), ("offset", C.c_uint64),
+                ("reduce", C.c_int32), ("reserved", C.c_int32)]
+
+
 class Stats(C.Structure):
     """tezgpu_stats (include/tezgpu.h)"""
     _fields_ = [("output_records", C.c_int64), ("output_bytes", C.c_int64), ("output_bytes_with_overhead", C.c_int64),
@@ -56,6 +62,12 @@ SYMBOLS = [
     ("tezgpu_sorter_reset", C.c_int32, [_V]),
     ("tezgpu_sorter_sort_device_fixed", C.c_int32, [_V, _V, _V, C.c_uint64, _V, C.c_uint64, _P(C.c_uint64), _V, _P(Stats)]),
     ("tezgpu_sorter_stream", _V, [_V]),
+    ("tezgpu_shuffle_header_size", C.c_uint64, [C.c_char_p, C.c_int64, C.c_int64, C.c_int32]),
+    ("tezgpu_shuffle_header_write", C.c_int32, [C.c_char_p, C.c_int64, C.c_int64, C.c_int32, _V, C.c_uint64, _P(C.c_uint64)]),
+    ("tezgpu_shuffle_header_read", C.c_int32, [_V, C.c_uint64, _V, C.c_uint64, _P(C.c_int64), _P(C.c_int64), _P(C.c_int32), _P(C.c_uint64)]),
+    ("tezgpu_shuffle_serve_bound", C.c_uint64, [C.c_char_p, _V, C.c_int32, C.c_int32]),
+    ("tezgpu_shuffle_serve", C.c_int32, [C.c_int32, _V, _V, C.c_char_p, C.c_int32, C.c_int32, _V, C.c_uint64, _P(C.c_uint64), _V]),
+    ("tezgpu_shuffle_receive", C.c_int32, [_V, C.c_uint64, _V, C.c_uint32, _P(C.c_uint32)]),
     ("tezgpu_debug_crc_emulate", C.c_uint32, [_V, C.c_uint64, C.c_uint32, C.c_uint32]),
     ("tezgpu_debug_chunk_fold_emulate", C.c_uint32, [_V, C.c_uint32, C.c_int32]),
     ("tezgpu_debug_runs_assemble_emulate", C.c_uint32, [_V, C.c_uint32, _V, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _V, C.c_uint32]),

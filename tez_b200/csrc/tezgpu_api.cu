@@ -502,6 +502,8 @@ int32_t tezgpu_fetch_segments_verified(int32_t device, const tezgpu_fetch_segmen
   TG_API_END
 }
 
+#include "shuffle_wire.inl"
+
 // Host emulation of the emit kernel's parallel CRC scheme (interleaved per-thread streams over the 4-byte words of a
 // piece, power-table alignment, xor-fold of piece contributions into the segment remainder, final conditioning).
 // Pure host arithmetic on the same tables the device uses; lets the CPU test-suite check the GF(2) algebra.

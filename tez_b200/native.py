@@ -300,3 +300,56 @@ def fetch_ranges(ranges, device=0, stream=None):
     ms = C.c_float()
     check(L.tezgpu_fetch_ranges(device, arr, len(ranges), stream, C.byref(ms)))
     return ms.value
+
+
+# ---------------------------------------------------------------- ShuffleHandler <-> fetcher wire format
+def shuffle_header(map_id, part_len, raw_len, reduce):
+    """ShuffleHeader.write (OG/ShuffleHeader.java:101-106) -> bytes."""
+    L = _lib.load()
+    mid = map_id.encode("utf-8")
+    buf = (C.c_uint8 * (len(mid) + 64))()
+    n = C.c_uint64()
+    check(L.tezgpu_shuffle_header_write(mid, part_len, raw_len, reduce, buf, len(buf), C.byref(n)))
+    assert n.value == L.tezgpu_shuffle_header_size(mid, part_len, raw_len, reduce)
+    return bytes(buf[:n.value])
+
+
+def read_shuffle_header(data):
+    """ShuffleHeader.readFields -> (map_id, part_len, raw_len, reduce, header bytes consumed)."""
+    L = _lib.load()
+    mid = C.create_string_buffer(1008)
+    pl, rl, rd, used = C.c_int64(), C.c_int64(), C.c_int32(), C.c_uint64()
+    raw = bytes(data)
+    check(L.tezgpu_shuffle_header_read(raw, len(raw), mid, len(mid), C.byref(pl), C.byref(rl), C.byref(rd), C.byref(used)))
+    return mid.value.decode("utf-8"), pl.value, rl.value, rd.value, used.value
+
+
+def shuffle_serve(d_file_out, index, map_id, reduce0, nreduce, device=0, stream=None):
+    """Response body ShuffleHandler sends for reducers [reduce0, reduce0 + nreduce) of one map output whose file.out is in
+    device memory (d_file_out = device pointer, index = (P, 3) int64 spill index) -> bytes."""
+    L = _lib.load()
+    idx = np.ascontiguousarray(index, dtype=np.int64)
+    mid = map_id.encode("utf-8")
+    cap = L.tezgpu_shuffle_serve_bound(mid, idx.ctypes.data, reduce0, nreduce)
+    out = np.empty(max(1, cap), dtype=np.uint8)
+    n = C.c_uint64()
+    check(L.tezgpu_shuffle_serve(device, d_file_out, idx.ctypes.data, mid, reduce0, nreduce, out.ctypes.data, cap, C.byref(n), stream))
+    return out[:n.value].tobytes()
+
+
+def shuffle_receive(body):
+    """Splits a response body into [(map_id, reduce, raw_len, segment bytes)] the way FetcherOrderedGrouped.copyMapOutput
+    walks it (header, then compressedLength bytes)."""
+    L = _lib.load()
+    raw = bytes(body)
+    n = C.c_uint32()
+    cap = 64
+    while True:
+        tab = (_lib.WireSegment * cap)()
+        rc = L.tezgpu_shuffle_receive(raw, len(raw), tab, cap, C.byref(n))
+        if rc != 0 and n.value > cap:
+            cap = n.value
+            continue
+        check(rc)
+        break
+    return [(s.map_id.decode("utf-8"), s.reduce, s.raw_len, raw[s.offset:s.offset + s.part_len]) for s in tab[:n.value]]
