@@ -350,12 +350,19 @@ def single_gpu(args):
             esteps -= esteps % slots
             out_bytes = [0] * slots
 
+            # one transfer at a time per PCIe direction: a slot's upload then runs at the link's full rate next to the
+            # other slot's download (the probe, tools/pcie_probe.py: 55.6 / 54.3 GB/s alone, 46 + 46 GB/s together),
+            # instead of both slots uploading and then both downloading at the same moments
+            up, down = threading.Lock(), threading.Lock()
+
             def e2e_worker(k, nsteps):
                 s2, ho = sorters[k], h_outs[k].numpy()
                 for _ in range(nsteps):
                     s2.reset()
-                    s2.collect_fixed(h_kv.data_ptr(), n=n)
-                    out, _, _, _ = s2.flush_to_memory(out=ho)
+                    with up:
+                        s2.collect_fixed(h_kv.data_ptr(), n=n)
+                    with down:
+                        out, _, _, _ = s2.flush_to_memory(out=ho)
                     out_bytes[k] = int(len(out))
 
             def run_e2e(nsteps_per_slot):
@@ -531,7 +538,7 @@ def main():
                     help="CPU arm: records per PipelinedSorter task (> 2^20 so that every task has two spans and its SpanMerger runs)")
     ap.add_argument("--cpu-single-records", type=int, default=10_000_000,
                     help="reference arm: records of the single-sorter sample (0 = skip)")
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-g1-pipeline", action="store_true")
     ap.add_argument("--config", type=int, default=2,

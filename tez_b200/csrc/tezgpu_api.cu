@@ -374,6 +374,16 @@ int32_t tezgpu_peer_close(int32_t device, void *dptr) {
   TG_API_END
 }
 
+}  // extern "C"
+// TEZGPU_FETCH_CTAS (read at every call): upper bound on the pull kernels' grid.  The pull is NVLink-bound; when it runs
+// next to another stream's HBM-bound kernels (TEZ_SHUFFLE_OVERLAP: the sort of the next batch) a grid that fills every
+// SM makes the two serialise, a grid of about one CTA per SM leaves room for the other kernels' CTAs.
+static uint32_t fetch_grid_cap(uint32_t grid) {
+  const char *e = getenv("TEZGPU_FETCH_CTAS");
+  const long cap = e ? atol(e) : 0;
+  return cap > 0 && (uint32_t)cap < grid ? (uint32_t)cap : grid;
+}
+extern "C" {
 int32_t tezgpu_fetch_ranges(int32_t device, const tezgpu_copy_range *ranges, uint32_t n, void *stream, float *ms_kernel) {
   TG_API_BEGIN
   TG_CHECK(ranges || n == 0, TEZGPU_E_INVALID, "null argument");
@@ -408,7 +418,8 @@ int32_t tezgpu_fetch_ranges(int32_t device, const tezgpu_copy_range *ranges, uin
   if (err == cudaSuccess) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(chunks, (uint64_t)sms * 2);
+    uint32_t grid = (uint32_t)std::min<uint64_t>(chunks, (uint64_t)sms * 2);
+    grid = fetch_grid_cap(grid);
     if (d_fr) {
       k_fetch_ranges<<<grid, FETCH_THREADS, 0, st>>>(d_fr, n, chunks);
     } else {
@@ -485,7 +496,7 @@ int32_t tezgpu_fetch_segments_verified(int32_t device, const tezgpu_fetch_segmen
   int sms = 148, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fetch_verify, FV_THREADS, 0);
-  const uint32_t grid = (uint32_t)std::min<uint64_t>(np, (uint64_t)sms * (per_sm > 0 ? per_sm : 1));
+  const uint32_t grid = fetch_grid_cap((uint32_t)std::min<uint64_t>(np, (uint64_t)sms * (per_sm > 0 ? per_sm : 1)));
   k_fetch_verify<<<grid, FV_THREADS, 0, st>>>(sc.segs.as<FetchSeg>(), sc.piece_start.as<uint32_t>(), n, np, d_crc, sc.piece_crc.as<TileCrc>());
   if (ms_kernel) cudaEventRecord(e1, st);
   k_crc_combine<<<(uint32_t)div_up(np, 256), 256, 0, st>>>(sc.piece_crc.as<TileCrc>(), np, d_crc, sc.seg_crc.as<uint32_t>());

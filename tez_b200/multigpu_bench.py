@@ -108,6 +108,9 @@ def run(args, workload_config, ClockSampler, hbm_peak, run_cpu, host_cores, veri
     overlap = px is not None and os.environ.get("TEZ_SHUFFLE_OVERLAP", "0") == "1"
     if overlap:
         import threading
+        # a pull grid that fills every SM serialises with the sort kernels instead of overlapping (measured: exchange =
+        # sort + pull); about one CTA per SM keeps NVLink busy and leaves the other half of each SM to the sort
+        os.environ.setdefault("TEZGPU_FETCH_CTAS", "148")
         pull_stream = torch.cuda.Stream(device=dev)
         pending = {}
 
