@@ -43,7 +43,8 @@ constexpr uint64_t PW_BAD = ~0ull - 1;    // the walk that produced this entry m
 constexpr uint32_t PW_TAIL = 2048;         // k_parse_guess looks for agreeing candidates in a window's last bytes first
 constexpr uint32_t PW_TAIL_TRIES = 512;    // candidate offsets tried there
 constexpr uint32_t PW_TAIL_MIN_RECS = 24;  // ... and the records a candidate walk must cover to count
-constexpr uint32_t PW_ALT_WAIT = 4;        // rounds a repeat-state agreement waits for a plain-state one
+constexpr uint32_t PW_ALT_WAIT = 4;        // rounds a strong exit that is not a plain-state agreement waits for one
+constexpr uint32_t PW_STRONG = 6;          // records a candidate walk must cover for its exit to count as strong evidence
 constexpr int PW_GUESS_THREADS = 128;      // k_parse_guess: four windows per CTA, one warp each
 constexpr int PW_CHASE_WARPS = 4;          // segments per CTA of k_parse_chase
 
@@ -208,10 +209,10 @@ __device__ __forceinline__ PwWalk pw_walk(const uint8_t *__restrict__ seg, const
 //   * EOF markers count only where a well-formed body has them (its last two bytes);
 //   * an exit beyond the NEXT window is only the fallback (records longer than a window are rare; when they exist every
 //     walk on the true chain reports the same far exit and the fallback is right);
-//   * the answer is the first exit that TWO surviving candidates agree on, exits in the plain reader state first
-//     (CPU emulation of these rules: 0 of 254 windows wrong on word-count data, 0 of 101 on 80-byte binary records,
-//     10 % on long run-length encoded runs, most on 4 KB random-byte values -- where a window holds 8 records and the
-//     chase's second walk costs nothing).
+//   * exits are ranked by evidence (agreement of two candidates, reader state, records covered; see the kernel).
+//     CPU emulation of these rules, wrong guesses per windows tested: word-count text 0/60, long run-length encoded
+//     runs of small records 0/60, 80-byte binary records 0/60, 4 KB values of one hot key (encoded run) 0/36, Zipf-like
+//     mix of encoded 4 KB records 0/22, unique 4 KB random-byte values 3/36.
 // Exactness never rests on any of this (k_parse_chase) -- only the number of windows walked a second time does.
 __global__ void __launch_bounds__(PW_GUESS_THREADS)
     k_parse_guess(const uint8_t *__restrict__ data, const PwSeg *__restrict__ segs, uint32_t nseg, uint32_t nwin_total,
@@ -232,13 +233,13 @@ __global__ void __launch_bounds__(PW_GUESS_THREADS)
     if (lane == 0) entry_out[w + 1] = pw_walk<false>(seg, sd, s, wend, false, sd.body0 << 1, 0, ~0ull, 0, none).exit_v;
     return;
   }
-  uint64_t far = PW_BAD, seen0 = PW_BAD, seen1 = PW_BAD, seen2 = PW_BAD, result = PW_BAD, alt = PW_BAD;
-  uint32_t round = 0, alt_round = 0;
+  uint64_t far = PW_BAD, seen0 = PW_BAD, seen1 = PW_BAD, seen2 = PW_BAD, result = PW_BAD, alt = PW_BAD, weak = PW_BAD;
+  uint32_t round = 0, alt_round = 0, alt_n = 0, weak_n = 0;
   bool done = false;
   // Phase A: candidates in the window's last PW_TAIL bytes -- a walk that falls into step with the true chain there
   // reaches the window's end after a few dozen records instead of a thousand; only walks of >= PW_TAIL_MIN_RECS records
-  // count (a start inside the last records "survives" by a single hop).  Phase B (when A found no agreement: records
-  // of a hundred bytes and more, long encoded runs): candidates from the window's start, as far as PW_MAX_TRIES.
+  // count (a start inside the last records "survives" by a single hop).  Phase B (when A found nothing: records of a
+  // hundred bytes and more, long encoded runs): candidates from the window's start, as far as PW_MAX_TRIES.
   const uint64_t tail0 = wend - ws > PW_TAIL ? wend - PW_TAIL : ws;
   const uint32_t tries_a = tail0 > ws ? PW_TAIL_TRIES : 0u;
   for (uint32_t t = 0; t < tries_a + PW_MAX_TRIES && !done; t += 16, round++) {
@@ -251,8 +252,10 @@ __global__ void __launch_bounds__(PW_GUESS_THREADS)
     }
     const uint64_t start = base + (lane >> 1);
     uint64_t x = PW_BAD;
+    uint32_t nrec = 0;
     if (start < wend) {
       const PwWalk r = pw_walk<false>(seg, sd, s, wend, false, (start << 1) | (uint64_t)(lane & 1u), 0, ~0ull, 0, none);
+      nrec = r.n;
       x = (r.early_eof || r.n < (phase_a ? PW_TAIL_MIN_RECS : 2u)) ? PW_BAD : r.exit_v;
       if (x == PW_EOF) x = PW_BAD;            // EOF inside a window that is not the last one
     }
@@ -263,20 +266,30 @@ __global__ void __launch_bounds__(PW_GUESS_THREADS)
     if (far == PW_BAD && fm) far = __shfl_sync(0xffffffffu, x, __ffs((int)fm) - 1);
     const uint32_t nm = __ballot_sync(0xffffffffu, near);
     if (nm) {
-      uint32_t cnt = 0;
-      if (near) cnt = (uint32_t)__popc(__match_any_sync(nm, x)) + ((x == seen0 || x == seen1 || x == seen2) ? 1u : 0u);
-      // an agreed exit in the plain reader state is taken at once; one in the "previous record was a repeat" state
-      // (the family of walks that hop over value lengths and merge with each other) only if nothing better turns up
-      // within PW_ALT_WAIT more rounds -- in run-length encoded data it is the true one
-      const uint32_t am0 = __ballot_sync(0xffffffffu, near && cnt >= 2 && (x & 1ull) == 0);
-      const uint32_t am1 = __ballot_sync(0xffffffffu, near && cnt >= 2 && (x & 1ull) != 0);
+      bool agreed = false;
+      if (near) agreed = __popc(__match_any_sync(nm, x)) + ((x == seen0 || x == seen1 || x == seen2) ? 1 : 0) >= 2;
+      // The evidence for an exit: how many candidates report it, in which reader state, and how many records the walk
+      // covered (in random bytes a wrong walk of k records has probability ~0.3^k; in text every byte is a plausible
+      // length, but there the true chain is found at once).
+      //   strong (>= PW_STRONG records) + agreed + plain state        -> taken at once
+      //   strong otherwise (agreed in the repeat state, or alone)    -> best of them taken PW_ALT_WAIT rounds later
+      //   weak agreed                                                -> only if nothing strong turns up at all
+      const bool strong = near && nrec >= PW_STRONG;
+      const uint32_t am0 = __ballot_sync(0xffffffffu, strong && agreed && (x & 1ull) == 0);
       if (am0) {
         result = __shfl_sync(0xffffffffu, x, __ffs((int)am0) - 1);
         done = true;
       } else {
-        if (am1 && alt == PW_BAD) {
-          alt = __shfl_sync(0xffffffffu, x, __ffs((int)am1) - 1);
-          alt_round = round;
+        const uint32_t ks = __reduce_max_sync(0xffffffffu, strong ? ((min(nrec, 0x3FFFFFFu) << 5) | (31u - lane)) : 0u);
+        if (ks && (ks >> 5) > alt_n) {
+          if (alt == PW_BAD) alt_round = round;
+          alt = __shfl_sync(0xffffffffu, x, 31 - (int)(ks & 31u));
+          alt_n = ks >> 5;
+        }
+        const uint32_t kw = __reduce_max_sync(0xffffffffu, (near && agreed && !strong) ? ((nrec << 5) | (31u - lane)) : 0u);
+        if (kw && (kw >> 5) > weak_n) {
+          weak = __shfl_sync(0xffffffffu, x, 31 - (int)(kw & 31u));
+          weak_n = kw >> 5;
         }
         for (uint32_t m = nm; m && seen2 == PW_BAD; m &= m - 1) {   // remember up to three lone survivors
           const uint64_t v = __shfl_sync(0xffffffffu, x, __ffs((int)m) - 1);
@@ -292,7 +305,7 @@ __global__ void __launch_bounds__(PW_GUESS_THREADS)
       done = true;
     }
   }
-  if (!done) result = alt != PW_BAD ? alt : (seen0 != PW_BAD ? seen0 : far);
+  if (!done) result = alt != PW_BAD ? alt : (weak != PW_BAD ? weak : (seen0 != PW_BAD ? seen0 : far));
   if (lane == 0) entry_out[w + 1] = result;
 }
 
