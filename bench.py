@@ -350,10 +350,15 @@ def single_gpu(args):
             esteps -= esteps % slots
             out_bytes = [0] * slots
 
-            # one transfer at a time per PCIe direction: a slot's upload then runs at the link's full rate next to the
-            # other slot's download (the probe, tools/pcie_probe.py: 55.6 / 54.3 GB/s alone, 46 + 46 GB/s together),
-            # instead of both slots uploading and then both downloading at the same moments
-            up, down = threading.Lock(), threading.Lock()
+            # --e2e-direction-locks: one transfer at a time per PCIe direction (a slot's upload next to the other slot's
+            # download; the link does 55.6 / 54.3 GB/s alone, 46 + 46 GB/s together: tools/pcie_probe.py).  Measured
+            # SLOWER than letting the two slots run free (286 vs 240 ms per step), hence off; tools/e2e_probe.py prints
+            # the timeline of both.
+            class _free:
+                def __enter__(self): return self
+                def __exit__(self, *a): return False
+            up = threading.Lock() if args.e2e_direction_locks else _free()
+            down = threading.Lock() if args.e2e_direction_locks else _free()
 
             def e2e_worker(k, nsteps):
                 s2, ho = sorters[k], h_outs[k].numpy()
@@ -540,6 +545,7 @@ def main():
                     help="reference arm: records of the single-sorter sample (0 = skip)")
     ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-direction-locks", action="store_true", help="e2e leg: serialise the task slots per PCIe direction")
     ap.add_argument("--no-g1-pipeline", action="store_true")
     ap.add_argument("--config", type=int, default=2,
                     help="2 (default, the driver's line), 1 (OrderedWordCount through the plugin mirror), 3 (k-way merge) or "
