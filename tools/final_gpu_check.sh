@@ -1,8 +1,8 @@
 #!/bin/bash
-# one GPU-side validation pass of the current tree: full GPU suite, the opt-in emit variants, A/B timings
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-TEZGPU_EMIT_ROUND_FILL=1 python -m pytest tests/test_sorter_gpu.py tests/test_merger_gpu.py tests/test_runtime_library_gpu.py -x -q 2>&1 | tail -1
-TEZGPU_EMIT_PIPE_UNALIGNED=1 python -m pytest tests/test_merger_gpu.py tests/test_peer_fetch_gpu.py tests/test_runtime_library_gpu.py tests/test_sorter_gpu.py -x -q 2>&1 | tail -1
-python tools/ab_emit.py default
-TEZGPU_EMIT_ROUND_FILL=1 python tools/ab_emit.py default
-TEZGPU_EMIT_PIPE_UNALIGNED=1 python tools/merge_profile.py 2>&1 | tail -1
+# last GPU call of the round: smoke, full parity suite, the N=1 bench line and the reference arm
+mkdir -p gpurun_out
+(timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -3) > gpurun_out/r2_final_smoke.log
+(timeout 1700 python -m pytest tests -m gpu -q --timeout 900 2>&1 | tail -40) > gpurun_out/r2_final_tests.log
+(timeout 900 python bench.py 2>&1 | tail -n 3 | cut -c1-7000) > gpurun_out/r2_final_bench.log
+(timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -n 2 | cut -c1-4000) > gpurun_out/r2_final_ref.log
+cat gpurun_out/r2_final_smoke.log; tail -5 gpurun_out/r2_final_tests.log; cat gpurun_out/r2_final_bench.log; cat gpurun_out/r2_final_ref.log
