@@ -360,18 +360,23 @@ def single_gpu(args):
             up = threading.Lock() if args.e2e_direction_locks else _free()
             down = threading.Lock() if args.e2e_direction_locks else _free()
 
-            def e2e_worker(k, nsteps):
+            def e2e_worker(k, nsteps, go, uploaded):
                 s2, ho = sorters[k], h_outs[k].numpy()
-                for _ in range(nsteps):
+                go.wait()       # tasks do not start in the same instant: slot k+1 starts when slot k has uploaded its
+                for i in range(nsteps):   # first input, so one slot's upload runs next to the other's download from step 0
                     s2.reset()
                     with up:
                         s2.collect_fixed(h_kv.data_ptr(), n=n)
+                    if i == 0:
+                        uploaded.set()
                     with down:
                         out, _, _, _ = s2.flush_to_memory(out=ho)
                     out_bytes[k] = int(len(out))
 
             def run_e2e(nsteps_per_slot):
-                ths = [threading.Thread(target=e2e_worker, args=(k, nsteps_per_slot)) for k in range(slots)]
+                ev = [threading.Event() for _ in range(slots + 1)]
+                ev[0].set()
+                ths = [threading.Thread(target=e2e_worker, args=(k, nsteps_per_slot, ev[k], ev[k + 1])) for k in range(slots)]
                 for t in ths:
                     t.start()
                 for t in ths:

@@ -31,15 +31,23 @@ def run(mode, steps):
         def __enter__(self): return self
         def __exit__(self, *a): return False
 
+    ev = [threading.Event() for _ in range(3)]
+    ev[0].set()
+    if mode != "stagger":
+        ev[1].set()
+
     def worker(k):
         s, ho = sorters[k], h_outs[k].numpy()
+        ev[k].wait()
         for i in range(steps):
             s.reset()
-            with (up if mode != "free" else nolock()):
+            with (up if mode == "locked" else nolock()):
                 t0 = time.perf_counter()
                 s.collect_fixed(h_kv.data_ptr(), n=n)
                 t1 = time.perf_counter()
-            with (down if mode != "free" else nolock()):
+            if i == 0:
+                ev[k + 1].set()
+            with (down if mode == "locked" else nolock()):
                 t2 = time.perf_counter()
                 out, _, _, st = s.flush_to_memory(out=ho)
                 t3 = time.perf_counter()
@@ -60,6 +68,7 @@ def run(mode, steps):
 
 run("free", 1)      # warm-up
 run("free", 3)
+run("stagger", 5)
 run("locked", 3)
 # single slot alone: the rates without any concurrency
 sorters[1].reset()
