@@ -681,8 +681,17 @@ class Merger {
     PwArrays none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // guess -> evaluate from the guessed entries -> chase the true chain (parse_windows.cuh); one host round trip
     TG_CUDA(cudaMemsetAsync(d_pwflags.p, 0, 64, st));
+    PwFixedHint hint{0, 0, 0, 0};
+    if (fixed_klen + fixed_vlen > 0 && vint_size_u32(fixed_klen) + vint_size_u32(fixed_vlen) <= 7) {
+      int b = 0;
+      for (int i = 0; i < vint_size_u32(fixed_klen); i++) hint.full |= (uint64_t)vint_byte_u32(fixed_klen, i) << (8 * b++);
+      for (int i = 0; i < vint_size_u32(fixed_vlen); i++) hint.full |= (uint64_t)vint_byte_u32(fixed_vlen, i) << (8 * b++);
+      hint.full_len = (uint32_t)b;
+      for (int i = 0; i < vint_size_u32(fixed_vlen); i++) hint.rep |= (uint64_t)vint_byte_u32(fixed_vlen, i) << (8 * i);
+      hint.rep_len = (uint32_t)vint_size_u32(fixed_vlen);
+    }
     k_parse_guess<<<(uint32_t)div_up((uint64_t)nwin * 32, PW_GUESS_THREADS), PW_GUESS_THREADS, 0, st>>>(data, d_pwseg.as<PwSeg>(), nseg, nwin,
-                                                                                                        d_entry[0].as<uint64_t>());
+                                                                                                        d_entry[0].as<uint64_t>(), hint);
     k_parse_windows<1><<<grid, PW_THREADS, 0, st>>>(data, d_pwseg.as<PwSeg>(), nseg, nwin, d_entry[0].as<uint64_t>(),
                                                     d_entry[1].as<uint64_t>(), d_wcount.as<uint32_t>(), d_wlast.as<uint64_t>(),
                                                     nullptr, d_pwflags.as<int>(), nullptr, nullptr, none);

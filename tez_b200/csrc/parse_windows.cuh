@@ -198,6 +198,28 @@ __device__ __forceinline__ PwWalk pw_walk(const uint8_t *__restrict__ seg, const
   return r;
 }
 
+// When the caller declared fixed key / value lengths (tezgpu_conf.fixed_*_len) but the segments could not be addressed
+// in place (run-length encoded inputs), the first bytes of a record are one of four known patterns.  The guess tests a
+// candidate start against them before walking it: garbage starts (multi-KB values are mostly garbage starts) cost two
+// compares instead of a walk of divergent lanes.  A hint only -- a wrong guess costs time, never correctness.
+struct PwFixedHint {
+  uint64_t full;      // vint(klen) vint(vlen), little endian in the low full_len bytes
+  uint64_t rep;       // vint(vlen)
+  uint32_t full_len, rep_len;   // 0 = no hint
+  __device__ __forceinline__ static bool starts_with(uint64_t x, uint64_t pat, uint32_t len) {
+    return len >= 8 ? x == pat : ((x ^ pat) & ((1ull << (8 * len)) - 1ull)) == 0;
+  }
+  // x = the 8 bytes at the candidate start; state 1 = the previous record was a repeat
+  __device__ __forceinline__ bool plausible(uint64_t x, uint32_t state) const {
+    if (full_len == 0) return true;
+    const uint32_t b0 = (uint32_t)(x & 0xFF);
+    if (state == 0)   // key length + value length, or RLE_MARKER (0xFE = vint -2) + value length
+      return starts_with(x, full, full_len) || (b0 == 0xFEu && starts_with(x >> 8, rep, rep_len));
+    // repeat state: value length, or V_END_MARKER (0xFD = vint -3) + key length + value length
+    return starts_with(x, rep, rep_len) || (b0 == 0xFDu && starts_with(x >> 8, full, full_len));
+  }
+};
+
 // Guess of a window's exit without knowing its entry (k_parse_guess, one WARP per window): candidate starts ws, ws+1,
 // ... in both reader states are walked to the window's end, 32 candidates at a time (lane l: offset l/2, state l&1).
 // Almost every wrong start dies within a few records (a byte decoded as a negative or absurd length); one that
@@ -216,7 +238,7 @@ __device__ __forceinline__ PwWalk pw_walk(const uint8_t *__restrict__ seg, const
 // Exactness never rests on any of this (k_parse_chase) -- only the number of windows walked a second time does.
 __global__ void __launch_bounds__(PW_GUESS_THREADS)
     k_parse_guess(const uint8_t *__restrict__ data, const PwSeg *__restrict__ segs, uint32_t nseg, uint32_t nwin_total,
-                  uint64_t *__restrict__ entry_out) {
+                  uint64_t *__restrict__ entry_out, PwFixedHint hint) {
   const uint32_t w = (blockIdx.x * PW_GUESS_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= nwin_total) return;
   const uint32_t s = pw_seg_of(segs, nseg, w);
@@ -253,7 +275,7 @@ __global__ void __launch_bounds__(PW_GUESS_THREADS)
     const uint64_t start = base + (lane >> 1);
     uint64_t x = PW_BAD;
     uint32_t nrec = 0;
-    if (start < wend) {
+    if (start < wend && hint.plausible(pw_load8(seg, start, sd.len), lane & 1u)) {
       const PwWalk r = pw_walk<false>(seg, sd, s, wend, false, (start << 1) | (uint64_t)(lane & 1u), 0, ~0ull, 0, none);
       nrec = r.n;
       x = (r.early_eof || r.n < (phase_a ? PW_TAIL_MIN_RECS : 2u)) ? PW_BAD : r.exit_v;
