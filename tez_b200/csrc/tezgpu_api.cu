@@ -113,20 +113,6 @@ __global__ void k_rebase_offsets(const uint32_t *__restrict__ key_off, const uin
   vlen[i] = vl;
 }
 
-// Host <-> device copies of whole task inputs / outputs go out in pieces: a single multi-GB cudaMemcpyAsync can hold
-// its DMA engine for 150 ms, and a copy in the OTHER direction submitted meanwhile by another task slot was measured to
-// make no progress at all until it finished (tools/e2e_probe.py: download 297 ms = 144 ms waiting + 153 ms alone).
-// Pieces give the two directions a hand-over point every few milliseconds.
-static const size_t COPY_PIECE = 64ull << 20;
-static cudaError_t copy_in_pieces(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
-  for (size_t o = 0; o < bytes; o += COPY_PIECE) {
-    const size_t m = std::min(COPY_PIECE, bytes - o);
-    cudaError_t e = cudaMemcpyAsync((uint8_t *)dst + o, (const uint8_t *)src + o, m, kind, st);
-    if (e != cudaSuccess) return e;
-  }
-  return cudaSuccess;
-}
-
 extern "C" {
 
 const char *tezgpu_last_error(void) { return g_last_error.c_str(); }
@@ -199,7 +185,7 @@ int32_t tezgpu_sorter_collect_batch(tezgpu_sorter *h, const uint8_t *kv, uint64_
   if (partition) h->d_part.grow_preserve((h->n + n) * 4, h->n * 4, st);
   h->d_tmp.ensure((size_t)n * 12);
   uint32_t *t = h->d_tmp.as<uint32_t>();
-  TG_CUDA(copy_in_pieces(h->d_kv.as<uint8_t>() + base, kv, kv_bytes, cudaMemcpyHostToDevice, st));
+  TG_CUDA(cudaMemcpyAsync(h->d_kv.as<uint8_t>() + base, kv, kv_bytes, cudaMemcpyHostToDevice, st));
   TG_CUDA(cudaMemcpyAsync(t, key_off, (size_t)n * 4, cudaMemcpyHostToDevice, st));
   TG_CUDA(cudaMemcpyAsync(t + n, val_off, (size_t)n * 4, cudaMemcpyHostToDevice, st));
   TG_CUDA(cudaMemcpyAsync(t + 2 * (size_t)n, val_len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
@@ -244,7 +230,7 @@ int32_t tezgpu_sorter_collect_fixed(tezgpu_sorter *h, const uint8_t *kv, const i
   TG_CUDA(cudaSetDevice(h->pipe.conf.device));
   h->d_kv.grow_preserve((h->n + n) * stride + 32, h->n * stride, st);
   if (partition) h->d_part.grow_preserve((h->n + n) * 4, h->n * 4, st);
-  TG_CUDA(copy_in_pieces(h->d_kv.as<uint8_t>() + h->n * stride, kv, n * stride, cudaMemcpyHostToDevice, st));
+  TG_CUDA(cudaMemcpyAsync(h->d_kv.as<uint8_t>() + h->n * stride, kv, n * stride, cudaMemcpyHostToDevice, st));
   if (partition)
     TG_CUDA(cudaMemcpyAsync(h->d_part.as<int32_t>() + h->n, partition, n * 4, cudaMemcpyHostToDevice, st));
   TG_CUDA(cudaStreamSynchronize(st));
@@ -276,7 +262,9 @@ static void sorter_run(tezgpu_sorter *h, uint8_t *host_out, uint64_t out_cap, ui
   st.output_bytes = (int64_t)h->payload_bytes;
   TG_CHECK(len <= out_cap, TEZGPU_E_NOMEM, "output buffer too small for file.out");
   if (len) {
-    TG_CUDA(copy_in_pieces(host_out, h->d_out.p, len, cudaMemcpyDeviceToHost, h->pipe.stream));
+    // one copy, not pieces: with 64 MB pieces a download running next to another task slot's upload was measured at
+    // 26 GB/s (312 ms) instead of 40-47 GB/s (tools/e2e_probe.py, profiles/r02_e2e_probe*.log)
+    TG_CUDA(cudaMemcpyAsync(host_out, h->d_out.p, len, cudaMemcpyDeviceToHost, h->pipe.stream));
     TG_CUDA(cudaStreamSynchronize(h->pipe.stream));
   }
   if (out_len) *out_len = len;
