@@ -18,6 +18,26 @@
 
 namespace tezgpu {
 
+// Small device -> host results (flags, counters, the spill index) are WRITTEN BY A KERNEL into mapped pinned memory
+// instead of going through cudaMemcpyAsync: a tiny copy is queued on a copy engine, and when another task slot's
+// multi-GB upload occupies that engine the sort's one host round trip waits for all of it (measured: a flush next to
+// another slot's upload took 297 ms = 144 ms behind the upload + 153 ms of its own; tools/e2e_probe.py).
+__global__ void k_store_to_host(uint32_t *__restrict__ dst0, const uint32_t *__restrict__ src0, uint32_t n0, uint32_t *__restrict__ dst1,
+                                const uint32_t *__restrict__ src1, uint32_t n1, uint32_t *__restrict__ dst2,
+                                const uint32_t *__restrict__ src2, uint32_t n2) {
+  for (uint32_t i = threadIdx.x; i < n0; i += blockDim.x) dst0[i] = src0[i];
+  for (uint32_t i = threadIdx.x; i < n1; i += blockDim.x) dst1[i] = src1[i];
+  for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) dst2[i] = src2[i];
+  __threadfence_system();
+}
+// up to three word-aligned ranges; dst = cudaHostAlloc memory (device-accessible under unified addressing)
+static inline void store_to_host(cudaStream_t st, void *d0, const void *s0, size_t b0, void *d1 = nullptr, const void *s1 = nullptr,
+                                 size_t b1 = 0, void *d2 = nullptr, const void *s2 = nullptr, size_t b2 = 0) {
+  k_store_to_host<<<1, 256, 0, st>>>((uint32_t *)d0, (const uint32_t *)s0, (uint32_t)(b0 / 4), (uint32_t *)d1, (const uint32_t *)s1,
+                                     (uint32_t)(b1 / 4), (uint32_t *)d2, (const uint32_t *)s2, (uint32_t)(b2 / 4));
+}
+
+
 static inline int partition_bits(int P) {
   int b = 0;
   while ((1ll << b) < (long long)P) b++;
@@ -343,10 +363,9 @@ class SortPipeline {
       }
       TG_CUDA(cudaGetLastError());
       uint32_t *hw = h_small.as<uint32_t>();
-      TG_CUDA(cudaMemcpyAsync(hw, small.as<uint32_t>() + 2064, 32, cudaMemcpyDeviceToHost, stream));
-      TG_CUDA(cudaMemcpyAsync(hw + 8, d_m_ptr, 4, cudaMemcpyDeviceToHost, stream));
-      if (state.spec_layout)
-        TG_CUDA(cudaMemcpyAsync(h_small.as<uint8_t>() + 4096, d_index.p, (size_t)P * 24, cudaMemcpyDeviceToHost, stream));
+      store_to_host(stream, hw, small.as<uint32_t>() + 2064, 32, hw + 8, d_m_ptr, 4, h_small.as<uint8_t>() + 4096, d_index.p,
+                    state.spec_layout ? (size_t)P * 24 : 0);
+      TG_CUDA(cudaGetLastError());
       TG_CUDA(cudaStreamSynchronize(stream));
       // words: [0] error, [1] large groups, [2..3] duplicates, [4..7] layout totals, [8] tied records
       TG_CHECK(!(hw[0] & 1u), TEZGPU_E_INVALID, "Illegal partition (outside [0, numPartitions))");
@@ -515,8 +534,8 @@ class SortPipeline {
       k_layout<<<1, 1024, 0, stream>>>(e, seg_start.as<uint64_t>(), tile_start.as<uint32_t>(), d_index.as<int64_t>(), d_totals());
       launches++;
       TG_CUDA(cudaGetLastError());
-      TG_CUDA(cudaMemcpyAsync(&hs[0], d_totals(), 16, cudaMemcpyDeviceToHost, stream));
-      TG_CUDA(cudaMemcpyAsync(h_small.as<uint8_t>() + 4096, d_index.p, (size_t)P * 24, cudaMemcpyDeviceToHost, stream));
+      store_to_host(stream, &hs[0], d_totals(), 16, h_small.as<uint8_t>() + 4096, d_index.p, (size_t)P * 24);
+      TG_CUDA(cudaGetLastError());
       TG_CUDA(cudaStreamSynchronize(stream));
       state.spec_layout = false;  // the device layout now belongs to this emit
     }
