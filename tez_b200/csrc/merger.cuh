@@ -734,7 +734,7 @@ class Merger {
     launches++;
     TG_CUDA(cudaMemsetAsync(d_pwflags.p, 0, 64, st));
     unsigned long long *d_kv_total = reinterpret_cast<unsigned long long *>(d_pwflags.as<int>() + 8);
-    k_parse_windows<2><<<(uint32_t)div_up((uint64_t)nwin * 32, PW_THREADS), PW_THREADS, 0, st>>>(data, d_pwseg.as<PwSeg>(), nseg, nwin, d_entry[cur].as<uint64_t>(), nullptr, nullptr, nullptr,
+    k_parse_windows<2><<<(uint32_t)div_up((uint64_t)nwin * PW_EMIT_GROUP, PW_THREADS), PW_THREADS, 0, st>>>(data, d_pwseg.as<PwSeg>(), nseg, nwin, d_entry[cur].as<uint64_t>(), nullptr, nullptr, nullptr,
                                                        d_kv_total, d_pwflags.as<int>(), d_wbase.as<uint64_t>(), carry, pa);
     launches++;
     TG_CUDA(cudaGetLastError());

@@ -45,6 +45,7 @@ constexpr uint32_t PW_TAIL_TRIES = 512;    // candidate offsets tried there
 constexpr uint32_t PW_TAIL_MIN_RECS = 24;  // ... and the records a candidate walk must cover to count
 constexpr uint32_t PW_ALT_WAIT = 4;        // rounds a strong exit that is not a plain-state agreement waits for one
 constexpr uint32_t PW_STRONG = 6;          // records a candidate walk must cover for its exit to count as strong evidence
+constexpr uint32_t PW_EMIT_GROUP = 8;      // lanes that walk one window together in the metadata pass (power of two)
 constexpr int PW_GUESS_THREADS = 128;      // k_parse_guess: four windows per CTA, one warp each
 constexpr int PW_CHASE_WARPS = 4;          // segments per CTA of k_parse_chase
 
@@ -133,15 +134,17 @@ struct PwWalk {
 };
 
 // the sequential reader over one window, from entry e
-// EMIT: all 32 lanes of a warp walk the SAME window from the same entry (identical control flow, broadcast loads) and
-// lane (record number mod 32) writes that record's metadata: consecutive records go out from consecutive lanes within
-// a few iterations, so every 32-byte sector of the six output arrays is completed while it is still in L2.  (One
-// THREAD per window had 483 k windows x 6 arrays = 2.9 M concurrent write streams -- 370 MB of open cache lines, more
-// than the L2 -- and the kernel ran at 140 GB/s of useful writes.)
+// EMIT: PW_EMIT_GROUP lanes walk the SAME window from the same entry (identical control flow, broadcast loads) and lane
+// (record number mod PW_EMIT_GROUP) writes that record's metadata: consecutive records go out from consecutive lanes
+// within a few iterations, so every 32-byte sector of the six output arrays is completed while it is still in L2.
+// One THREAD per window had 483 k windows x 6 arrays = 2.9 M concurrent write streams -- 370 MB of open cache lines,
+// more than the L2 -- and ran at 140 GB/s of useful writes (144 ms of config 3's step); a whole warp per window
+// removed that but issued every walk instruction once per window instead of once per 32 windows (109 ms).  Groups of
+// eight lanes keep four windows per warp and ~230 k open lines (29 MB).
 template <bool EMIT>
 __device__ __forceinline__ PwWalk pw_walk(const uint8_t *__restrict__ seg, const PwSeg &sd, uint32_t s, uint64_t wend, bool last_win,
                                           uint64_t e, uint64_t base, uint64_t carry_off, uint64_t carry_len, const PwArrays &out,
-                                          uint32_t lane = 0) {
+                                          uint32_t lane = 0) {  // lane: position inside the emit group
   PwWalk r;
   r.exit_v = e;
   r.n = 0;
@@ -186,7 +189,7 @@ __device__ __forceinline__ PwWalk pw_walk(const uint8_t *__restrict__ seg, const
     if (q + (uint64_t)vl > sd.body_end) { status = 2; break; }
     if (EMIT) {
       const uint64_t rr = base + r.n;
-      if (((uint32_t)rr & 31u) == lane) {
+      if (((uint32_t)rr & (PW_EMIT_GROUP - 1u)) == lane) {
         out.key_off[rr] = sd.off + orig_koff;
         out.val_off[rr] = sd.off + q;
         out.key_len[rr] = (uint32_t)orig_klen;
@@ -341,8 +344,8 @@ __global__ void __launch_bounds__(PW_GUESS_THREADS)
 
 //   MODE 1  evaluate (one thread per window): walks from the presumed entry; stores the exit, the record count and the
 //           last full key.
-//   MODE 2  emit (one warp per window, see pw_walk): entries are final (k_parse_chase); writes the per-record metadata
-//           at rec_base[w]...
+//   MODE 2  emit (PW_EMIT_GROUP lanes per window, see pw_walk): entries are final (k_parse_chase); writes the per-record
+//           metadata at rec_base[w]...
 template <int MODE>
 __global__ void __launch_bounds__(PW_THREADS)
     k_parse_windows(const uint8_t *__restrict__ data, const PwSeg *__restrict__ segs, uint32_t nseg,
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(PW_THREADS)
                     const uint64_t *__restrict__ rec_base, const uint64_t *__restrict__ carry /*[2*nwin]*/, PwArrays out) {
   constexpr bool EMIT = MODE == 2;
   const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t w = EMIT ? gt >> 5 : gt, lane = threadIdx.x & 31;
+  const uint32_t w = EMIT ? gt / PW_EMIT_GROUP : gt, lane = threadIdx.x & (PW_EMIT_GROUP - 1u);
   uint64_t my_bytes = 0;
   if (w < nwin_total) {
     const uint32_t s = pw_seg_of(segs, nseg, w);
