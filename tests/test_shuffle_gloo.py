@@ -138,3 +138,17 @@ def test_peer_exchange_fails_on_every_rank_or_none():
     for r in range(world):
         assert ret[r].startswith("RuntimeError: peer pull unavailable"), ret[r]
         assert ret["sum%d" % r] == 3
+
+
+def test_verified_pull_visits_producers_in_ring_order():
+    """shuffle.ring_order: the rows of the segment table (ordered by source rank for the merge's tie-breaking) are pulled
+    producer rank+1 first, so that at any moment a producer serves one consumer."""
+    from tez_b200 import shuffle
+    world, P = 8, 16
+    for rank in range(world):
+        segs = [(1000 * g + p, 10 + p, p, g) for g in range(world) for p in range(P // world * 0, 2)]
+        order = shuffle.ring_order(segs, rank, world)
+        assert [t[3] for t in order] == [g % world for g in range(rank + 1, rank + world) for _ in range(2)]
+        assert all(t[3] != rank for t in order) and len(order) == 2 * (world - 1)
+        for g in range(world):
+            assert [t[2] for t in order if t[3] == g] == sorted(t[2] for t in order if t[3] == g)
