@@ -97,12 +97,11 @@ class ClockSampler:
 
 
 def cpu_sample(cores, per_task):
-    """Bounded sample of the same workload for the CPU arm: `cores` independent PipelinedSorter tasks."""
-    import torch
-    from tez_b200 import synth
+    """Bounded sample of the same workload for the CPU arm: `cores` independent PipelinedSorter tasks.  Same bytes as
+    synth.gen_c2 (tests/test_synth.py), from the oracle's C generator on all cores (the torch CPU path needs minutes)."""
+    from oracle import tez_oracle as O
     n = cores * per_task
-    kv = synth.gen_c2(0, n, seed=2, device="cpu").numpy()
-    return kv, n
+    return O.gen_c2(0, n, seed=2, threads=cores), n
 
 
 def run_cpu(cores, per_task, steps, warmup, partitions):
@@ -168,8 +167,7 @@ def single_sorter_cpu(records, partitions, threads, repeats=3):
     """The config-2 shape itself on the host: ONE PipelinedSorter over `records` records (spans of 2^20 records sorted
     by `threads` sort threads, SpanMerger heap over the spans, one IFile writer), `repeats` runs -> GB/s of each."""
     from oracle import tez_oracle as O
-    from tez_b200 import synth
-    kv = synth.gen_c2(0, records, seed=2, device="cpu").numpy()
+    kv = O.gen_c2(0, records, seed=2, threads=min(host_cores(), 32))
     conf = O.sorter_conf(partitions, sort_threads=threads)
     out = []
     for _ in range(repeats):

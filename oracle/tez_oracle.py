@@ -323,10 +323,25 @@ def merge(segments, cmp_kind, factor=100, sort_segments=False, check_for_same_ke
     return out
 
 
-def gen_c2(first_index, n, seed=2):
-    """SURVEY 8(d) C2 generator: n records x 80 B (16 B key + 64 B value)."""
+def gen_c2(first_index, n, seed=2, threads=1):
+    """SURVEY 8(d) C2 generator: n records x 80 B (16 B key + 64 B value); threads > 1 fills slices concurrently (every
+    record is a function of (seed, index) alone)."""
     out = np.empty(n * 80, dtype=np.uint8)
-    lib().tzo_gen_c2(out.ctypes.data, first_index, n, seed)
+    L = lib()
+    if threads <= 1 or n < (1 << 20):
+        L.tzo_gen_c2(out.ctypes.data, first_index, n, seed)
+        return out
+    from concurrent.futures import ThreadPoolExecutor
+    per = -(-n // threads)
+    base = out.ctypes.data
+
+    def fill(t):
+        a, b = t * per, min(n, (t + 1) * per)
+        if b > a:
+            L.tzo_gen_c2(base + a * 80, first_index + a, b - a, seed)    # ctypes releases the GIL
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(fill, range(threads)))
     return out
 
 
