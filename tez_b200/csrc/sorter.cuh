@@ -74,7 +74,7 @@ class SortPipeline {
 
   // workspace (grow-only, reused across flushes)
   DeviceBuffer keysA, keysB, valsA, valsB, same, blk, small, tile_state, sizes, rec_off;
-  DeviceBuffer t_pos[2], t_gid[2], t_lidx[2], t_key64[2], t_val[2], t_state, t_ghead, t_gneq, sym_sets, sym_tab;
+  DeviceBuffer t_pos[2], t_gid[2], t_lidx[2], t_key64[2], t_val[2], t_state, t_ghead, t_gneq, sym_sets, sym_tab, rep_flags;
   DeviceBuffer seg_start, tile_start, part_start, d_index, seg_crc, tile_desc, tile_crc, tie_state;
   PinnedBuffer h_small;
 
@@ -520,6 +520,10 @@ class SortPipeline {
         sizes.ensure(n4);
         rec_off.ensure(((size_t)n + 2) * 8);
         if (n) {
+          rep_flags.ensure(n);
+          k_emit_repeat_flags<<<(uint32_t)div_up(n, 256), 256, 0, stream>>>(e, K, rep_flags.as<uint8_t>());
+          launches++;
+          e.rep = rep_flags.as<uint8_t>();
           k_emit_sizes<<<(uint32_t)div_up(n, 256), 256, 0, stream>>>(e, K, sizes.as<uint32_t>());
           k_sum_u32_blocks<<<nblk, SCAN_THREADS, 0, stream>>>(sizes.as<uint32_t>(), n, blk.as<uint64_t>());
           k_scan_block_sums<<<1, 1024, 0, stream>>>(blk.as<uint64_t>(), nblk);

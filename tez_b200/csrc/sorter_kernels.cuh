@@ -696,6 +696,7 @@ struct EmitParams {
   int send_empty;
   int unordered;       // UnorderedPartitionedKVWriter.mergeAll: partitions without records get an all-zero index entry
   int P;
+  const uint8_t *rep;  // optional, [n]: emit_is_repeat() of every sorted position, computed once (k_emit_repeat_flags)
 };
 
 // Is the record at sorted position r written as a repeat of the previous key ([RLE_MARKER] vint(vlen) value)?
@@ -705,6 +706,7 @@ struct EmitParams {
 //          from its own segment, or the top segment changed and the comparator reports equality
 //          (SORT/TezMerger.java:215-245,597-652) -- and the writer's own test applies on top when it was built with rle.
 __device__ __forceinline__ bool emit_is_repeat(const EmitParams &e, uint32_t r, uint32_t ps) {
+  if (e.rep) return e.rep[r] != 0;   // k_emit_sizes and k_emit ask twice per record each: one gather pass instead of four
   if (r == ps || !e.same[r]) return false;
   const Records &rec = e.rec;
   const uint32_t i = e.order[r];
@@ -718,6 +720,17 @@ __device__ __forceinline__ bool emit_is_repeat(const EmitParams &e, uint32_t r, 
   const uint32_t tag = record_tag(rec, i);
   if (writer || (tag & 1u)) return true;
   return e.check_same && ((tag >> 1) != (record_tag(rec, e.order[r - 1]) >> 1));
+}
+
+// emit_is_repeat() of every sorted position, once: the rule gathers the record's lengths and the tags of two records,
+// and both k_emit_sizes and k_emit need it for r and r-1 (merging word counts: 6e8 records, ~6 random sector reads per
+// evaluation)
+__global__ void __launch_bounds__(256) k_emit_repeat_flags(EmitParams e, const uint32_t *__restrict__ K, uint8_t *__restrict__ flags) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= e.rec.n) return;
+  const int sh = 32 - e.rec.pbits;
+  const uint32_t p = e.rec.pbits ? (K[r] >> sh) : 0;
+  flags[r] = emit_is_repeat(e, r, e.part_start[p]) ? 1 : 0;    // e.rep is null here: the rule itself
 }
 
 // var mode: emitted size of the record at sorted position r (IFile.Writer.writeKVPair / writeValue / markers,
