@@ -19,3 +19,11 @@ def test_hash_partition_matches_oracle():
     got = synth.hash_partition(keys, 64).numpy()
     exp = np.array([O.partition_of(O.CMP_BYTES, kv[i, :16].tobytes(), 64) for i in range(500)])
     assert np.array_equal(got, exp)
+
+
+def test_threaded_c_generator_gives_the_same_bytes():
+    """bench.py's CPU arm fills its sample with the oracle's C generator on many threads (slices are independent)."""
+    import numpy as np
+    from oracle import tez_oracle as O
+    n = (1 << 20) + 12345
+    assert np.array_equal(O.gen_c2(7, n, seed=2, threads=5), O.gen_c2(7, n, seed=2))
