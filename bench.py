@@ -388,7 +388,7 @@ def single_gpu(args):
             e2e = {"value": round(n * REC / t / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": n * REC,
                    "d2h_bytes_per_step": out_bytes[0], "ms_per_step": round(t * 1e3, 2), "steps": esteps,
                    "task_slots": slots, "host_cpus_pinned_to_gpu_numa_node": len(numa.cpus) if numa.cpus else None,
-                   "api": "tezgpu_sorter_collect_fixed + tezgpu_sorter_flush_to_memory (pinned host buffers), 2 task slots"}
+                   "api": "tezgpu_sorter_collect_fixed + tezgpu_sorter_flush_to_memory (pinned host buffers), 2 task slots, the second one starts after the first one's first upload"}
             for s2 in sorters:
                 s2.close()
             del h_kv, h_outs
